@@ -1,0 +1,184 @@
+"""Pins the CPU oracle (oracle/balm_oracle.c).
+
+The reference has no tests or golden vectors, so the oracle is pinned by:
+  1. an independent numpy restatement (tests/numpy_ref.py),
+  2. finite differences of the cost  sum_v coe_v * lambda_min  under the left perturbation
+     R <- Exp(phi) R, p <- Exp(phi) p + dt  (bavoxel.hpp:1123-1125),
+  3. the gauge identities  g . dT = 0,  dT^T H dT = 0  for a common left perturbation
+     (Supplementary eq. 170-185),
+  4. residual(left_evaluate_acc2) == residual(evaluate_only_residual) when fix.N = 0,
+  5. end-to-end: LM converges to the noise floor on the benchmark_virtual scene.
+"""
+import numpy as np
+import pytest
+
+import numpy_ref
+import scenes
+from oracle import oracle_py as orc
+
+
+def _oracle(sc, **kw):
+    return orc.Oracle(sc["n_poses"], sc["row_ptr"], sc["pose_idx"], sc["obs10"], sc["coe"], sc["fix10"], **kw)
+
+
+@pytest.fixture(scope="module")
+def small():
+    return scenes.make_scene(n_poses=6, n_planes=40, seed=10)
+
+
+def test_exp_log_roundtrip():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        phi = rng.normal(0, 0.5, 3)
+        R = orc.exp_so3(phi)
+        assert np.allclose(R, scenes.exp_so3(phi), atol=1e-15)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-14)
+        assert np.allclose(orc.log_so3(R), phi, atol=1e-12)
+    assert np.array_equal(orc.exp_so3([0, 0, 1e-12]), np.eye(3))  # tools.hpp:60 threshold
+
+
+def test_eig3_matches_numpy():
+    rng = np.random.default_rng(1)
+    for t in range(200):
+        B = rng.normal(size=(3, 3))
+        A = B @ B.T if t % 2 else B + B.T
+        if t % 5 == 0:  # near-degenerate planar covariance, the case that matters (lambda_min ~ 1e-4)
+            Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            A = Q @ np.diag([1e-4, 0.083, 0.0831]) @ Q.T
+        lam, U = orc.eig3(A)
+        ref = np.linalg.eigvalsh(A)
+        assert np.allclose(lam, ref, rtol=0, atol=1e-14 * max(1, np.abs(ref).max()))
+        assert np.allclose(U.T @ U, np.eye(3), atol=1e-14)
+        assert np.allclose(A @ U, U * lam, atol=1e-13 * max(1, np.abs(ref).max()))
+
+
+def test_cluster_transform_is_moment_of_transformed_points():
+    rng = np.random.default_rng(2)
+    pts = rng.normal(size=(17, 3))
+    R = scenes.exp_so3(rng.normal(size=3))
+    p = rng.normal(size=3)
+    sc = dict(n_poses=1, row_ptr=np.array([0, 1]), pose_idx=np.array([0], dtype=np.int32),
+              obs10=np.array([[0] * 10], dtype=float), coe=np.array([1.0]), fix10=None)
+    P = pts.T @ pts
+    v = pts.sum(0)
+    o = np.array([P[0, 0], P[0, 1], P[0, 2], P[1, 1], P[1, 2], P[2, 2], v[0], v[1], v[2], 17.0])
+    Pw, vw, n = numpy_ref._world_cluster(o, scenes.pack_poses([R], [p])[0])
+    w = pts @ R.T + p
+    assert np.allclose(Pw, w.T @ w, atol=1e-12) and np.allclose(vw, w.sum(0), atol=1e-12)
+
+
+@pytest.mark.parametrize("drop,with_fix", [(0.0, False), (0.4, False), (0.0, True), (0.3, True)])
+def test_oracle_matches_numpy_restatement(drop, with_fix):
+    sc = scenes.make_scene(n_poses=7, n_planes=30, seed=3, drop=drop, with_fix=with_fix)
+    o = _oracle(sc)
+    for include_fix in ([False, True] if with_fix else [False]):
+        H, g, r = o.evaluate(sc["poses_init"], include_fix=include_fix)
+        Hn, gn, rn = numpy_ref.evaluate(sc, sc["poses_init"], include_fix=include_fix)
+        sH = np.abs(Hn).max()
+        assert abs(r - rn) <= 1e-12 * abs(rn)
+        assert np.abs(g - gn).max() <= 1e-10 * np.abs(gn).max()
+        assert np.abs(H - Hn).max() <= 1e-10 * sH
+        assert np.abs(H - H.T).max() <= 1e-12 * sH
+    assert abs(o.residual(sc["poses_init"]) - numpy_ref.residual(sc, sc["poses_init"])) <= 1e-12 * abs(rn)
+
+
+def test_residual_of_hessian_pass_equals_residual_only(small):
+    o = _oracle(small)
+    _, _, r = o.evaluate(small["poses_init"])
+    assert abs(r - o.residual(small["poses_init"])) <= 1e-13 * abs(r)
+
+
+def _perturbed(poses, dx):
+    out = np.zeros_like(poses)
+    for i in range(len(poses)):
+        R, p = scenes.unpack_pose(poses[i])
+        dR = scenes.exp_so3(dx[6 * i:6 * i + 3])
+        out[i] = scenes.pack_poses([dR @ R], [dR @ p + dx[6 * i + 3:6 * i + 6]])[0]
+    return out
+
+
+def test_gradient_and_hessian_vs_finite_differences(small):
+    o = _oracle(small)
+    x0 = small["poses_init"]
+    H, g, _ = o.evaluate(x0)
+    n = 6 * small["n_poses"]
+    rng = np.random.default_rng(5)
+    # directional derivatives along random directions (central differences)
+    for _ in range(4):
+        d = rng.normal(size=n)
+        d /= np.linalg.norm(d)
+        h = 1e-5
+        fp, fm = o.residual(_perturbed(x0, h * d)), o.residual(_perturbed(x0, -h * d))
+        f0 = o.residual(x0)
+        assert abs((fp - fm) / (2 * h) - g @ d) <= 1e-6 * np.linalg.norm(g)
+        h2 = 1e-3
+        fp, fm = o.residual(_perturbed(x0, h2 * d)), o.residual(_perturbed(x0, -h2 * d))
+        # second directional derivative of the cost along an Exp-path equals d^T H d (left perturbation)
+        assert abs((fp - 2 * f0 + fm) / h2 ** 2 - d @ H @ d) <= 2e-4 * np.abs(H).max()
+    # per-coordinate gradient
+    for c in rng.choice(n, 6, replace=False):
+        e = np.zeros(n)
+        e[c] = 1e-6
+        fd = (o.residual(_perturbed(x0, e)) - o.residual(_perturbed(x0, -e))) / 2e-6
+        assert abs(fd - g[c]) <= 1e-6 * np.abs(g).max()
+
+
+def test_gauge_nullspace(small):
+    """A common rigid left perturbation of all poses leaves the cost unchanged: g.dT=0, dT^T H dT = 0."""
+    o = _oracle(small)
+    H, g, _ = o.evaluate(small["poses_init"])
+    rng = np.random.default_rng(6)
+    six = rng.normal(size=6)
+    dT = np.tile(six, small["n_poses"])
+    assert abs(g @ dT) <= 1e-9 * np.abs(g).max() * np.linalg.norm(dT)
+    assert abs(dT @ H @ dT) <= 1e-9 * np.abs(H).max() * (dT @ dT)
+
+
+def test_thread_split_equals_single_range(small):
+    o = _oracle(small)
+    H1, g1, r1 = o.evaluate(small["poses_init"])
+    H4, g4, r4 = o.evaluate_threads(small["poses_init"], threads=4)
+    assert np.abs(H1 - H4).max() <= 1e-12 * np.abs(H1).max()
+    assert np.abs(g1 - g4).max() <= 1e-12 * np.abs(g1).max()
+    assert abs(r1 - r4) <= 1e-13 * abs(r1)
+    # head/end ranges add up (bavoxel.hpp:1045-1047 range semantics)
+    Ha, ga, ra = o.evaluate(small["poses_init"], 0, 13)
+    Hb, gb, rb = o.evaluate(small["poses_init"], 13, 40)
+    assert np.abs(Ha + Hb - H1).max() <= 1e-12 * np.abs(H1).max()
+    assert abs(ra + rb - r1) <= 1e-13 * abs(r1)
+
+
+def test_ldlt_solve_matches_numpy():
+    rng = np.random.default_rng(7)
+    B = rng.normal(size=(40, 40))
+    A = B @ B.T + 0.1 * np.eye(40)
+    b = rng.normal(size=40)
+    x, zp = orc.ldlt_solve(A, b)
+    assert zp == 0 and np.allclose(x, np.linalg.solve(A, b), rtol=1e-10, atol=1e-12)
+    # symmetric indefinite: Eigen's LDLT tolerates it (diagonal pivoting), so must the stand-in
+    A2 = B + B.T + np.diag(np.linspace(-30, 30, 40))
+    x2, _ = orc.ldlt_solve(A2, b)
+    assert np.allclose(A2 @ x2, b, atol=1e-8)
+
+
+def test_lm_converges_to_noise_floor():
+    sc = scenes.make_scene(n_poses=8, n_planes=60, seed=11)
+    o = _oracle(sc)
+    st, poses, tr, per_iter = o.damping_iter(sc["poses_init"], max_iter=20, u0=0.1, threads=1, gauge_mode=1)
+    assert st == 0 and len(tr) >= 3
+    assert tr[-1]["r2"] < 0.05 * tr[0]["r1"]
+    floor = sc["coe"].sum() * 0.01 ** 2  # sum_v coe_v * sigma^2, the point-noise floor of the cost
+    assert 0.7 * floor < tr[-1]["r2"] < 1.1 * floor
+    # ground truth re-expressed relative to pose 0 (what rsme compares against, benchmark_virtual.cpp:489)
+    rot0, tra0 = orc.rmse(sc["poses_init"], sc["poses_gt"])
+    rot, tra = orc.rmse(poses, sc["poses_gt"])
+    assert rot < 0.1 * rot0 and tra < 0.1 * tra0
+    assert rot * 57.3 < 0.1 and tra < 0.01
+    costs = [t["r2"] for t in tr if t["accepted"]]
+    assert all(b <= a for a, b in zip(costs, costs[1:]))
+
+
+def test_damping_iter_precheck_too_few_planes():
+    sc = scenes.make_scene(n_poses=4, n_planes=10, seed=12)
+    st, _, _, _ = _oracle(sc).damping_iter(sc["poses_init"])
+    assert st == 4  # reference prints and exit(0)s (bavoxel.hpp:1079-1085)
