@@ -1,0 +1,117 @@
+"""Thin object wrapper over the C ABI context (include/balm_b200.h)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """One GPU, one registered set of plane voxels, N poses."""
+
+    def __init__(self, n_poses, device=0, precision=L.PREC_FP64):
+        self._h = C.c_void_p()
+        self.N = int(n_poses)
+        self.n = 6 * self.N
+        L.check(L.lib().balm_create(C.byref(self._h), self.N, int(device), int(precision)))
+
+    def close(self):
+        if self._h:
+            L.lib().balm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- problem ----
+    def set_voxels(self, row_ptr, pose_idx, obs10, coe, fix10=None):
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        pose_idx = np.ascontiguousarray(pose_idx, dtype=np.int32)
+        obs10 = np.ascontiguousarray(obs10, dtype=np.float64)
+        coe = np.ascontiguousarray(coe, dtype=np.float64)
+        fix10 = None if fix10 is None else np.ascontiguousarray(fix10, dtype=np.float64)
+        self.M = len(row_ptr) - 1
+        L.check(L.lib().balm_set_voxels(self._h, self.M, _p(row_ptr), _p(pose_idx), _p(obs10), _p(fix10), _p(coe)))
+
+    def synth_virtual(self, n_voxels, first_voxel=0, pts_size=40, point_noise=0.01, surf_range=2.0, seed=10):
+        gt = np.zeros((self.N, 12))
+        init = np.zeros((self.N, 12))
+        L.check(L.lib().balm_synth_virtual(self._h, int(n_voxels), int(first_voxel), int(pts_size),
+                                           float(point_noise), float(surf_range), int(seed), _p(gt), _p(init)))
+        self.M = int(n_voxels)
+        return gt, init
+
+    def download_voxels(self):
+        K = L.lib().balm_num_obs(self._h)
+        row_ptr = np.zeros(self.M + 1, dtype=np.int64)
+        pose_idx = np.zeros(K, dtype=np.int32)
+        obs10 = np.zeros((K, 10))
+        coe = np.zeros(self.M)
+        L.check(L.lib().balm_download_voxels(self._h, _p(row_ptr), _p(pose_idx), _p(obs10), _p(coe)))
+        return row_ptr, pose_idx, obs10, coe
+
+    # ---- evaluation ----
+    def evaluate(self, poses12, head=0, end=None, include_fix=False, want_H=True):
+        poses12 = np.ascontiguousarray(poses12, dtype=np.float64)
+        H = np.zeros((self.n, self.n), order="F") if want_H else None
+        g = np.zeros(self.n)
+        r = C.c_double()
+        end = self.M if end is None else end
+        L.check(L.lib().balm_evaluate(self._h, _p(poses12), head, end, int(include_fix), _p(H), _p(g), C.byref(r)))
+        return H, g, r.value
+
+    def residual(self, poses12):
+        poses12 = np.ascontiguousarray(poses12, dtype=np.float64)
+        r = C.c_double()
+        L.check(L.lib().balm_residual(self._h, _p(poses12), C.byref(r)))
+        return r.value
+
+    def solve(self, u):
+        dx = np.zeros(self.n)
+        q1 = C.c_double()
+        bad = C.c_int()
+        L.check(L.lib().balm_solve(self._h, float(u), _p(dx), C.byref(q1), C.byref(bad)))
+        return dx, q1.value, bool(bad.value)
+
+    def damping_iter(self, poses12, max_iter=10, u0=0.01, v0=2.0, rel_tol=1e-6, hess_includes_fix=False,
+                     gauge_mode=0, min_planes_per_pose=20, verbose=False, want_per_iter=False):
+        poses = np.array(poses12, dtype=np.float64, order="C", copy=True)
+        opts = L.LmOpts(max_iter, u0, v0, rel_tol, int(hess_includes_fix), gauge_mode, min_planes_per_pose,
+                        int(verbose))
+        trace = (L.Trace * max_iter)()
+        n_it = C.c_int()
+        per_iter = np.zeros((max_iter, self.N, 12)) if want_per_iter else None
+        L.check(L.lib().balm_damping_iter(self._h, _p(poses), C.byref(opts), trace, C.byref(n_it), _p(per_iter)))
+        tr = [dict(r1=t.r1, r2=t.r2, u=t.u, v=t.v, q=t.q, q1=t.q1, accepted=bool(t.accepted),
+                   recomputed_hess=bool(t.recomputed_hess), not_pd=bool(t.not_pd)) for t in trace[:n_it.value]]
+        return poses, tr, (per_iter[:n_it.value] if want_per_iter else None)
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        L.check(L.lib().balm_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, rank, world, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        L.check(L.lib().balm_comm_init(self._h, int(rank), int(world), buf))
+
+    # ---- instrumentation ----
+    def timings(self):
+        t = L.Timings()
+        L.check(L.lib().balm_get_timings(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in L.Timings._fields_}
+
+    def reset_counters(self):
+        L.check(L.lib().balm_reset_counters(self._h))
+
+    def sync(self):
+        L.check(L.lib().balm_sync(self._h))

@@ -1,0 +1,584 @@
+// balm_api.cu -- C ABI of libbalm_b200.so (include/balm_b200.h): context, problem registration, the
+// evaluation pipeline, the damped solve and the Levenberg-Marquardt driver of BALM2::damping_iter
+// (/root/reference/src/benchmark/bavoxel.hpp:1069-1166).  Host code is plain C++; all arithmetic of the hot
+// path runs in the CUDA kernels of this directory.  There is no CPU fallback: without a CUDA device every
+// entry point fails with BALM_ERR_CUDA.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <vector>
+#include "internal.cuh"
+
+void synth_host_poses(int N, uint64_t seed, double *poses_gt, double *poses_init);
+
+static thread_local std::string g_err;
+void balm_set_error(const std::string &s) { g_err = s; }
+extern "C" const char *balm_last_error(void) { return g_err.c_str(); }
+extern "C" int balm_version(void) { return 100; }
+
+// ---------------- NCCL through dlopen (no link-time dependency) ----------------
+struct NcclDyn {
+  void *h = nullptr;
+  typedef struct { char internal[128]; } uid_t;
+  int (*GetUniqueId)(uid_t *) = nullptr;
+  int (*CommInitRank)(void **, int, uid_t, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (h) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+      h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) return false;
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  }
+};
+static NcclDyn g_nccl;
+
+// ---------------- helpers ----------------
+template <typename T>
+static int dev_alloc(T **p, size_t count) {
+  CUDA_TRY(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
+  return BALM_OK;
+}
+#define TRY(x)                \
+  do {                        \
+    int _s = (x);             \
+    if (_s != BALM_OK) return _s; \
+  } while (0)
+
+static void free_problem(balm_ctx *c) {
+  cudaFree(c->obs); cudaFree(c->pose_idx); cudaFree(c->row_ptr); cudaFree(c->coe); cudaFree(c->fix);
+  cudaFree(c->csc_ptr); cudaFree(c->csc_obs); cudaFree(c->csc_vox);
+  c->obs = nullptr; c->pose_idx = nullptr; c->row_ptr = nullptr; c->coe = nullptr; c->fix = nullptr;
+  c->csc_ptr = c->csc_obs = c->csc_vox = nullptr;
+  cudaFree(c->stats); cudaFree(c->G); cudaFree(c->obs_part); cudaFree(c->syrk_part);
+  c->stats = c->G = c->obs_part = c->syrk_part = nullptr;
+  tensor_syrk_free(c);
+  c->M = c->K = c->Kp = 0;
+}
+
+static int alloc_problem_arrays(balm_ctx *c, int64_t M, int64_t K, bool with_fix) {
+  free_problem(c);
+  c->M = M; c->K = K;
+  c->Kp = (K + 31) / 32 * 32;
+  TRY(dev_alloc(&c->obs, (size_t)10 * c->Kp));
+  TRY(dev_alloc(&c->pose_idx, (size_t)K));
+  TRY(dev_alloc(&c->row_ptr, (size_t)M + 1));
+  TRY(dev_alloc(&c->coe, (size_t)M));
+  if (with_fix) TRY(dev_alloc(&c->fix, (size_t)10 * M));
+  return BALM_OK;
+}
+
+// Workspaces that depend on the registered problem (batch size, split counts).
+static int alloc_workspaces(balm_ctx *c) {
+  size_t g_budget = (size_t)16 << 30;  // bytes for the fp64 G' batch
+  if (const char *e = getenv("BALM_G_BUDGET_MB")) g_budget = (size_t)atoll(e) << 20;  // tests: force batching
+  int64_t vb = (int64_t)(g_budget / ((size_t)3 * c->ldg * sizeof(double)));
+  if (vb > c->M) vb = c->M;
+  if (vb < 1) vb = 1;
+  if (!c->dense && vb < c->M) {
+    balm_set_error("sparse co-visibility problems must fit one evaluation batch");
+    return BALM_ERR_UNSUPPORTED;
+  }
+  c->VB = vb;
+  TRY(dev_alloc(&c->stats, (size_t)vb * BALM_STATS_STRIDE));
+  TRY(dev_alloc(&c->G, (size_t)3 * vb * c->ldg));
+  CUDA_TRY(cudaMemsetAsync(c->G, 0, sizeof(double) * (size_t)3 * vb * c->ldg, c->stream));  // zero the column padding
+  const int tiles_p = (c->N + 31) / 32;
+  c->obs_chunks = std::max(1, (c->sm_count * 16 + tiles_p - 1) / tiles_p);
+  if (c->obs_chunks > 4096) c->obs_chunks = 4096;
+  TRY(dev_alloc(&c->obs_part, (size_t)c->obs_chunks * BALM_ACC * c->Np));
+  CUDA_TRY(cudaMemsetAsync(c->obs_part, 0, sizeof(double) * (size_t)c->obs_chunks * BALM_ACC * c->Np, c->stream));
+  // SYRK work decomposition: (tile, k-split) items, sized so the last wave is nearly full
+  c->syrk_nb = c->ldg / BALM_SYRK_TILE;
+  c->syrk_tiles = c->syrk_nb * (c->syrk_nb + 1) / 2;
+  const int64_t rows = 3 * vb;
+  int max_splits = (int)std::max<int64_t>(1, std::min<int64_t>(rows / 512, 64));
+  const size_t part_budget = (size_t)3 << 30;
+  const size_t per_split = (size_t)c->syrk_tiles * BALM_SYRK_TILE * BALM_SYRK_TILE * sizeof(double);
+  max_splits = (int)std::max<size_t>(1, std::min<size_t>(max_splits, part_budget / per_split));
+  int best = 1;
+  double best_eff = 0;
+  for (int s = 1; s <= max_splits; s++) {
+    const int items = c->syrk_tiles * s;
+    const int waves = (items + c->sm_count - 1) / c->sm_count;
+    const double eff = (double)items / ((double)waves * c->sm_count);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  c->syrk_splits = best;
+  TRY(dev_alloc(&c->syrk_part, (size_t)best * c->syrk_tiles * BALM_SYRK_TILE * BALM_SYRK_TILE));
+  if (c->prec == BALM_PREC_TENSOR) TRY(tensor_syrk_init(c));
+  return BALM_OK;
+}
+
+// ---------------- ctx ----------------
+extern "C" int balm_create(balm_ctx **out, int n_poses, int device, int precision) {
+  if (!out || n_poses < 1) { balm_set_error("balm_create: bad arguments"); return BALM_ERR_INVALID; }
+  if (precision != BALM_PREC_FP64 && precision != BALM_PREC_TENSOR) {
+    balm_set_error("balm_create: unknown precision mode");
+    return BALM_ERR_INVALID;
+  }
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { balm_set_error("balm_create: no such CUDA device"); return BALM_ERR_CUDA; }
+  CUDA_TRY(cudaSetDevice(device));
+  balm_ctx *c = new balm_ctx();
+  c->N = n_poses; c->n = 6 * n_poses; c->device = device; c->prec = precision;
+  c->ldg = (c->n + BALM_SYRK_TILE - 1) / BALM_SYRK_TILE * BALM_SYRK_TILE;
+  c->Np = (n_poses + 31) / 32 * 32;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  const size_t n = c->n;
+  TRY(dev_alloc(&c->poses, 12 * (size_t)c->N));
+  TRY(dev_alloc(&c->poses_trial, 12 * (size_t)c->N));
+  TRY(dev_alloc(&c->H, n * n + n + 8));
+  c->g = c->H + n * n;
+  TRY(dev_alloc(&c->A, n * n));
+  TRY(dev_alloc(&c->W, n * BALM_NB));
+  TRY(dev_alloc(&c->dx, n));
+  TRY(dev_alloc(&c->dvec, n));
+  TRY(dev_alloc(&c->scal, 16));
+  TRY(dev_alloc(&c->flags, 4));
+  TRY(dev_alloc(&c->accum, (size_t)BALM_ACC * c->Np));
+  c->res_blocks = c->sm_count * 16;
+  TRY(dev_alloc(&c->res_part, (size_t)c->res_blocks));
+  CUDA_TRY(cudaMallocHost((void **)&c->h_scal, 16 * sizeof(double)));
+  CUDA_TRY(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int)));
+  for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+  *out = c;
+  return BALM_OK;
+}
+
+extern "C" int balm_destroy(balm_ctx *c) {
+  if (!c) return BALM_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_problem(c);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  cudaFree(c->poses); cudaFree(c->poses_trial); cudaFree(c->H); cudaFree(c->A); cudaFree(c->W);
+  cudaFree(c->dx); cudaFree(c->dvec); cudaFree(c->scal); cudaFree(c->flags); cudaFree(c->accum);
+  cudaFree(c->res_part);
+  cudaFreeHost(c->h_scal); cudaFreeHost(c->h_flags);
+  for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return BALM_OK;
+}
+
+// ---------------- problem registration ----------------
+static int finish_registration(balm_ctx *c, const std::vector<int64_t> &row_ptr, const std::vector<int32_t> &pidx) {
+  const int N = c->N;
+  const int64_t M = c->M;
+  std::vector<int> planes(N, 0);
+  bool dense = true;
+  int max_k = 0;
+  for (int64_t v = 0; v < M; v++) {
+    const int64_t k = row_ptr[v + 1] - row_ptr[v];
+    if (k > max_k) max_k = (int)k;
+    if (k != N) dense = false;
+    for (int64_t s = row_ptr[v]; s < row_ptr[v + 1]; s++) {
+      const int p = pidx[s];
+      if (p < 0 || p >= N || (s > row_ptr[v] && p <= pidx[s - 1])) {
+        balm_set_error("balm_set_voxels: pose_idx must be ascending and in [0,N) inside each voxel");
+        return BALM_ERR_INVALID;
+      }
+      planes[p]++;
+    }
+  }
+  c->dense = dense;
+  c->max_k = max_k;
+  c->min_planes = *std::min_element(planes.begin(), planes.end());
+  if (!dense) {  // pose-major lists for the observation pass
+    std::vector<int> ptr(N + 1, 0), cobs(c->K), cvox(c->K);
+    for (int i = 0; i < N; i++) ptr[i + 1] = ptr[i] + planes[i];
+    std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+    for (int64_t v = 0; v < M; v++)
+      for (int64_t s = row_ptr[v]; s < row_ptr[v + 1]; s++) {
+        const int p = pidx[s];
+        cobs[cur[p]] = (int)s;
+        cvox[cur[p]] = (int)v;
+        cur[p]++;
+      }
+    c->csc_max_len = *std::max_element(planes.begin(), planes.end());
+    TRY(dev_alloc(&c->csc_ptr, (size_t)N + 1));
+    TRY(dev_alloc(&c->csc_obs, (size_t)c->K));
+    TRY(dev_alloc(&c->csc_vox, (size_t)c->K));
+    CUDA_TRY(cudaMemcpyAsync(c->csc_ptr, ptr.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->csc_obs, cobs.data(), sizeof(int) * c->K, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->csc_vox, cvox.data(), sizeof(int) * c->K, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  return alloc_workspaces(c);
+}
+
+__global__ void aos_to_soa_kernel(const double *aos, double *soa, int64_t count, int64_t stride) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= count) return;
+#pragma unroll
+  for (int c = 0; c < 10; c++) soa[c * stride + s] = aos[s * 10 + c];
+}
+__global__ void soa_to_aos_kernel(const double *soa, double *aos, int64_t count, int64_t stride) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= count) return;
+#pragma unroll
+  for (int c = 0; c < 10; c++) aos[s * 10 + c] = soa[c * stride + s];
+}
+
+static int upload_aos(balm_ctx *c, const double *aos, bool aos_on_device, double *soa, int64_t count, int64_t stride) {
+  // stage the AoS records through a device scratch buffer and transpose on the GPU
+  const int64_t chunk = 1 << 22;
+  double *scratch = nullptr;
+  if (!aos_on_device) TRY(dev_alloc(&scratch, (size_t)std::min(chunk, count) * 10));
+  for (int64_t b = 0; b < count; b += chunk) {
+    const int64_t m = std::min(chunk, count - b);
+    const double *src = aos + b * 10;
+    if (!aos_on_device) {
+      CUDA_TRY(cudaMemcpyAsync(scratch, src, sizeof(double) * m * 10, cudaMemcpyHostToDevice, c->stream));
+      src = scratch;
+    }
+    aos_to_soa_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(src, soa + b, m, stride);
+    c->launches++;
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  cudaFree(scratch);
+  return BALM_OK;
+}
+
+extern "C" int balm_set_voxels(balm_ctx *c, int64_t M, const int64_t *row_ptr, const int32_t *pose_idx,
+                               const double *obs10, const double *fix10, const double *coe) {
+  if (!c || M < 1 || !row_ptr || !pose_idx || !obs10 || !coe) {
+    balm_set_error("balm_set_voxels: bad arguments");
+    return BALM_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int64_t K = row_ptr[M];
+  if (row_ptr[0] != 0 || K < M) { balm_set_error("balm_set_voxels: bad row_ptr"); return BALM_ERR_INVALID; }
+  if (K >= ((int64_t)1 << 31)) { balm_set_error("balm_set_voxels: more than 2^31 observations per GPU"); return BALM_ERR_UNSUPPORTED; }
+  TRY(alloc_problem_arrays(c, M, K, fix10 != nullptr));
+  CUDA_TRY(cudaMemcpyAsync(c->row_ptr, row_ptr, sizeof(int64_t) * (M + 1), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->pose_idx, pose_idx, sizeof(int32_t) * K, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->coe, coe, sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
+  TRY(upload_aos(c, obs10, false, c->obs, K, c->Kp));
+  if (fix10) TRY(upload_aos(c, fix10, false, c->fix, M, M));
+  std::vector<int64_t> rp(row_ptr, row_ptr + M + 1);
+  std::vector<int32_t> pi(pose_idx, pose_idx + K);
+  return finish_registration(c, rp, pi);
+}
+
+extern "C" int balm_set_voxels_dev(balm_ctx *c, int64_t M, const int64_t *row_ptr_dev, const int32_t *pose_idx_dev,
+                                   const double *obs10_dev, const double *fix10_dev, const double *coe_dev,
+                                   int64_t K) {
+  if (!c || M < 1 || !row_ptr_dev || !pose_idx_dev || !obs10_dev || !coe_dev || K < M) {
+    balm_set_error("balm_set_voxels_dev: bad arguments");
+    return BALM_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  TRY(alloc_problem_arrays(c, M, K, fix10_dev != nullptr));
+  CUDA_TRY(cudaMemcpyAsync(c->row_ptr, row_ptr_dev, sizeof(int64_t) * (M + 1), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->pose_idx, pose_idx_dev, sizeof(int32_t) * K, cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->coe, coe_dev, sizeof(double) * M, cudaMemcpyDeviceToDevice, c->stream));
+  TRY(upload_aos(c, obs10_dev, true, c->obs, K, c->Kp));
+  if (fix10_dev) TRY(upload_aos(c, fix10_dev, true, c->fix, M, M));
+  std::vector<int64_t> rp(M + 1);
+  std::vector<int32_t> pi(K);
+  CUDA_TRY(cudaMemcpy(rp.data(), c->row_ptr, sizeof(int64_t) * (M + 1), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(pi.data(), c->pose_idx, sizeof(int32_t) * K, cudaMemcpyDeviceToHost));
+  return finish_registration(c, rp, pi);
+}
+
+extern "C" int64_t balm_num_obs(balm_ctx *c) { return c ? c->K : 0; }
+
+extern "C" int balm_download_voxels(balm_ctx *c, int64_t *row_ptr, int32_t *pose_idx, double *obs10, double *coe) {
+  if (!c || !c->obs) { balm_set_error("balm_download_voxels: no voxels registered"); return BALM_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (row_ptr) CUDA_TRY(cudaMemcpy(row_ptr, c->row_ptr, sizeof(int64_t) * (c->M + 1), cudaMemcpyDeviceToHost));
+  if (pose_idx) CUDA_TRY(cudaMemcpy(pose_idx, c->pose_idx, sizeof(int32_t) * c->K, cudaMemcpyDeviceToHost));
+  if (coe) CUDA_TRY(cudaMemcpy(coe, c->coe, sizeof(double) * c->M, cudaMemcpyDeviceToHost));
+  if (obs10) {
+    const int64_t chunk = 1 << 22;
+    double *scratch = nullptr;
+    TRY(dev_alloc(&scratch, (size_t)std::min(chunk, c->K) * 10));
+    for (int64_t b = 0; b < c->K; b += chunk) {
+      const int64_t m = std::min(chunk, c->K - b);
+      soa_to_aos_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(c->obs + b, scratch, m, c->Kp);
+      CUDA_TRY(cudaMemcpyAsync(obs10 + b * 10, scratch, sizeof(double) * m * 10, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(scratch);
+  }
+  return BALM_OK;
+}
+
+extern "C" int balm_synth_virtual(balm_ctx *c, int64_t M, int64_t first_voxel, int pts, double noise, double range,
+                                  uint64_t seed, double *poses_gt, double *poses_init) {
+  if (!c || M < 1 || pts < 1) { balm_set_error("balm_synth_virtual: bad arguments"); return BALM_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int64_t K = M * c->N;
+  if (K >= ((int64_t)1 << 31)) { balm_set_error("balm_synth_virtual: more than 2^31 observations per GPU"); return BALM_ERR_UNSUPPORTED; }
+  std::vector<double> gt(12 * (size_t)c->N), init(12 * (size_t)c->N);
+  synth_host_poses(c->N, seed, gt.data(), init.data());
+  if (poses_gt) memcpy(poses_gt, gt.data(), sizeof(double) * gt.size());
+  if (poses_init) memcpy(poses_init, init.data(), sizeof(double) * init.size());
+  TRY(alloc_problem_arrays(c, M, K, false));
+  CUDA_TRY(cudaMemcpyAsync(c->poses_trial, gt.data(), sizeof(double) * gt.size(), cudaMemcpyHostToDevice, c->stream));
+  TRY(launch_synth(c, M, first_voxel, pts, noise, range, seed, c->poses_trial));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->dense = true;
+  c->max_k = c->N;
+  c->min_planes = (int)std::min<int64_t>(M, 1 << 30);
+  return alloc_workspaces(c);
+}
+
+// ---------------- evaluation ----------------
+static int allreduce_sum(balm_ctx *c, double *buf, size_t count) {
+  if (c->world <= 1 || !c->comm) return BALM_OK;
+  const int rc = g_nccl.AllReduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
+  if (rc != 0) {
+    balm_set_error(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    return BALM_ERR_NCCL;
+  }
+  return BALM_OK;
+}
+
+// H, g, r of voxels [head,end) at device poses `poses`; result in c->H | c->g | c->scal[0] (all-reduced).
+static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t end, bool include_fix) {
+  if (!c->obs) { balm_set_error("no voxels registered"); return BALM_ERR_INVALID; }
+  if (head < 0 || end > c->M || head > end) { balm_set_error("evaluate: bad voxel range"); return BALM_ERR_INVALID; }
+  double *r_dev = c->g + c->n;  // contiguous with H and g -> one all-reduce
+  CUDA_TRY(cudaMemsetAsync(r_dev, 0, sizeof(double), c->stream));
+  float ms;
+  c->tm.ms_stats = c->tm.ms_obs = c->tm.ms_syrk = c->tm.ms_slice = 0;
+  bool first = true;
+  if (head == end) {  // empty range: H = 0
+    CUDA_TRY(cudaMemsetAsync(c->H, 0, sizeof(double) * ((size_t)c->n * c->n + c->n + 1), c->stream));
+    return BALM_OK;
+  }
+  for (int64_t v0 = head; v0 < end; v0 += c->VB) {
+    const int64_t v1 = std::min(end, v0 + c->VB);
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    TRY(launch_voxel_stats(c, poses, v0, v1, true, include_fix, r_dev));
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    TRY(launch_obs_pass(c, poses, v0, v1, first));
+    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if (c->prec == BALM_PREC_TENSOR) TRY(launch_tensor_syrk(c, 3 * (v1 - v0), first));
+    else TRY(launch_syrk_f64(c, 3 * (v1 - v0), first));
+    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev[3]));
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->tm.ms_stats += ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->tm.ms_obs += ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->tm.ms_syrk += ms;
+    first = false;
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+  TRY(launch_assemble(c));
+  CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+  TRY(allreduce_sum(c, c->H, (size_t)c->n * c->n + c->n + 1));
+  CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->scal, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(cudaEventSynchronize(c->ev[6]));
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->tm.ms_assemble = ms;
+  cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); c->tm.ms_allreduce = ms;
+  return BALM_OK;
+}
+
+static int residual_dev(balm_ctx *c, const double *poses, double *host_out) {
+  if (!c->obs) { balm_set_error("no voxels registered"); return BALM_ERR_INVALID; }
+  double *r_dev = c->scal + 2;
+  CUDA_TRY(cudaEventRecord(c->ev[7], c->stream));
+  CUDA_TRY(cudaMemsetAsync(r_dev, 0, sizeof(double), c->stream));
+  TRY(launch_voxel_stats(c, poses, 0, c->M, false, true, r_dev));
+  TRY(allreduce_sum(c, r_dev, 1));
+  CUDA_TRY(cudaEventRecord(c->ev[8], c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_scal + 2, r_dev, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]);
+  c->tm.ms_residual = ms;
+  *host_out = c->h_scal[2];
+  return BALM_OK;
+}
+
+extern "C" int balm_evaluate(balm_ctx *c, const double *poses12, int64_t head, int64_t end, int include_fix,
+                             double *H, double *g, double *residual) {
+  if (!c || !poses12) { balm_set_error("balm_evaluate: bad arguments"); return BALM_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(c->poses, poses12, sizeof(double) * 12 * c->N, cudaMemcpyHostToDevice, c->stream));
+  TRY(evaluate_dev(c, c->poses, head, end, include_fix != 0));
+  const size_t n = c->n;
+  if (H) CUDA_TRY(cudaMemcpyAsync(H, c->H, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
+  if (g) CUDA_TRY(cudaMemcpyAsync(g, c->g, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (residual) *residual = c->h_scal[0];
+  return BALM_OK;
+}
+
+extern "C" int balm_residual(balm_ctx *c, const double *poses12, double *residual) {
+  if (!c || !poses12 || !residual) { balm_set_error("balm_residual: bad arguments"); return BALM_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(c->poses_trial, poses12, sizeof(double) * 12 * c->N, cudaMemcpyHostToDevice, c->stream));
+  return residual_dev(c, c->poses_trial, residual);
+}
+
+static int solve_dev(balm_ctx *c, double u, double *q1, int *not_pd) {
+  CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
+  TRY(launch_ldlt_solve(c, u));
+  CUDA_TRY(cudaEventRecord(c->ev[10], c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_scal + 1, c->scal + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]);
+  c->tm.ms_solve = ms;
+  *q1 = c->h_scal[1];
+  *not_pd = c->h_flags[0] != 0 || !std::isfinite(*q1);
+  return BALM_OK;
+}
+
+extern "C" int balm_solve(balm_ctx *c, double u, double *dx, double *q1, int *not_pd) {
+  if (!c) { balm_set_error("balm_solve: bad arguments"); return BALM_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  double q = 0;
+  int bad = 0;
+  TRY(solve_dev(c, u, &q, &bad));
+  if (dx) CUDA_TRY(cudaMemcpy(dx, c->dx, sizeof(double) * c->n, cudaMemcpyDeviceToHost));
+  if (q1) *q1 = q;
+  if (not_pd) *not_pd = bad;
+  return BALM_OK;
+}
+
+extern "C" void balm_default_lm_opts(balm_lm_opts *o) {
+  o->max_iter = 10; o->u0 = 0.01; o->v0 = 2; o->rel_tol = 1e-6; o->hess_includes_fix = 0; o->gauge_mode = 0;
+  o->min_planes_per_pose = 20; o->verbose = 0;
+}
+
+extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opts *o, balm_trace *trace, int *n_iters,
+                                 double *poses_per_iter) {
+  if (!c || !poses12 || !o) { balm_set_error("balm_damping_iter: bad arguments"); return BALM_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (n_iters) *n_iters = 0;
+  if (o->min_planes_per_pose > 0) {  // bavoxel.hpp:1071-1085 (the shim reproduces the printf + exit(0))
+    long long local_min = c->min_planes;
+    if (c->world > 1) {  // a pose may be seen from other ranks' shards: the guard is on the global count,
+      // which the caller checks; per-rank we only refuse when even the sum of shards cannot reach it.
+      local_min = (long long)c->min_planes * c->world;
+    }
+    if (local_min < o->min_planes_per_pose) {
+      balm_set_error("Initial error too large. Please loose plane determination criteria for more planes.");
+      return BALM_ERR_TOO_FEW_PLANES;
+    }
+  }
+  const size_t pbytes = sizeof(double) * 12 * c->N;
+  CUDA_TRY(cudaMemcpyAsync(c->poses, poses12, pbytes, cudaMemcpyHostToDevice, c->stream));
+  double u = o->u0, v = o->v0, r1 = 0, r2 = 0;
+  bool calc_hess = true;
+  float ms_update = 0;
+  for (int it = 0; it < o->max_iter; it++) {
+    if (calc_hess) {
+      TRY(evaluate_dev(c, c->poses, 0, c->M, o->hess_includes_fix != 0));
+      CUDA_TRY(cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      r1 = c->h_scal[0];
+    }
+    double q1 = 0;
+    int not_pd = 0;
+    TRY(solve_dev(c, u, &q1, &not_pd));
+    TRY(launch_pose_update(c, c->poses, c->dx, c->poses_trial));
+    TRY(residual_dev(c, c->poses_trial, &r2));
+    double q = r1 - r2;
+    if (not_pd || !std::isfinite(r2)) q = -1.0;  // unusable step -> rejected, u *= v
+    if (o->verbose)  // the reference's trace line (bavoxel.hpp:1132)
+      printf("iter%d: (%lf %lf) u: %lf v: %.1lf q: %.3lf %lf %lf\n", it, r1, r2, u, v, q / q1, q1, q);
+    balm_trace t{r1, r2, u, v, q, q1, 0, calc_hess ? 1 : 0, not_pd};
+    if (q > 0) {  // bavoxel.hpp:1134-1143
+      std::swap(c->poses, c->poses_trial);
+      const double rho = q / q1;
+      v = 2;
+      const double f = 1 - pow(2 * rho - 1, 3);
+      u *= (f < (1.0 / 3.0) ? (1.0 / 3.0) : f);
+      calc_hess = true;
+      t.accepted = 1;
+    } else {  // bavoxel.hpp:1144-1149
+      u = u * v;
+      v = 2 * v;
+      calc_hess = false;
+    }
+    if (trace) trace[it] = t;
+    if (poses_per_iter)
+      CUDA_TRY(cudaMemcpyAsync(poses_per_iter + (size_t)it * 12 * c->N, c->poses, pbytes, cudaMemcpyDeviceToHost, c->stream));
+    if (n_iters) *n_iters = it + 1;
+    if (o->rel_tol >= 0 && fabs(r1 - r2) / r1 < o->rel_tol) break;  // bavoxel.hpp:1155
+  }
+  if (o->gauge_mode == 0 || o->gauge_mode == 1) TRY(launch_gauge(c, c->poses, o->gauge_mode));
+  CUDA_TRY(cudaMemcpyAsync(poses12, c->poses, pbytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->tm.ms_update = ms_update;
+  return BALM_OK;
+}
+
+// ---------------- multi-GPU ----------------
+extern "C" int balm_comm_unique_id(void *out128) {
+  if (!out128) return BALM_ERR_INVALID;
+  if (!g_nccl.load()) { balm_set_error("libnccl.so.2 not found"); return BALM_ERR_NCCL; }
+  NcclDyn::uid_t id;
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) { balm_set_error("ncclGetUniqueId failed"); return BALM_ERR_NCCL; }
+  memcpy(out128, &id, 128);
+  return BALM_OK;
+}
+
+extern "C" int balm_comm_init(balm_ctx *c, int rank, int world, const void *unique_id128) {
+  if (!c || world < 1 || rank < 0 || rank >= world) { balm_set_error("balm_comm_init: bad arguments"); return BALM_ERR_INVALID; }
+  c->rank = rank; c->world = world;
+  if (world == 1) return BALM_OK;
+  if (!unique_id128) { balm_set_error("balm_comm_init: unique id required"); return BALM_ERR_INVALID; }
+  if (!g_nccl.load()) { balm_set_error("libnccl.so.2 not found"); return BALM_ERR_NCCL; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  NcclDyn::uid_t id;
+  memcpy(&id, unique_id128, 128);
+  const int rc = g_nccl.CommInitRank(&c->comm, world, id, rank);
+  if (rc != 0) {
+    balm_set_error(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    return BALM_ERR_NCCL;
+  }
+  return BALM_OK;
+}
+
+// ---------------- instrumentation ----------------
+extern "C" int balm_get_timings(balm_ctx *c, balm_timings *out) {
+  if (!c || !out) return BALM_ERR_INVALID;
+  *out = c->tm;
+  out->launches = (int)c->launches;
+  return BALM_OK;
+}
+extern "C" int balm_reset_counters(balm_ctx *c) {
+  if (!c) return BALM_ERR_INVALID;
+  c->launches = 0;
+  return BALM_OK;
+}
+extern "C" int balm_sync(balm_ctx *c) {
+  if (!c) return BALM_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return BALM_OK;
+}
+extern "C" int balm_device_views(balm_ctx *c, double **H_dev, double **g_dev) {
+  if (!c) return BALM_ERR_INVALID;
+  if (H_dev) *H_dev = c->H;
+  if (g_dev) *g_dev = c->g;
+  return BALM_OK;
+}

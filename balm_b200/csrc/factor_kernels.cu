@@ -1,0 +1,326 @@
+// factor_kernels.cu -- the O(K) streaming passes of the eigen-factor evaluation (HBM-bound kernels K1-K3).
+//
+//   voxel_stats_kernel : per voxel  C = sum_i T_i C_i T_i^T (+fix), v_bar, eig(A)  -> residual (+ stats table)
+//                        = VOX_HESS::evaluate_only_residual (bavoxel.hpp:428-470) and phase 1 of
+//                          left_evaluate_acc2 (bavoxel.hpp:322-360)
+//   obs_pass_kernel    : per observation  g_k^i, a_i, gradient and diagonal-block terms
+//                        = left_evaluate_acc2 per-observation loop (bavoxel.hpp:365-402); writes the scaled
+//                          factor matrix G' (3 rows per voxel, 6N columns) consumed by the SYRK
+//   obs_reduce_kernel  : fixed-order reduction of the per-chunk gradient / diagonal-block partials
+//
+// Layouts: observations SoA obs[c][s] (c<10, s in CSR order), so a warp reading 32 consecutive slots of one
+// voxel issues ten fully coalesced 256-byte requests; the stats table is AoS (20 doubles per voxel) because
+// the observation pass reads it warp-uniformly (one broadcast transaction per 16 bytes).
+#include "internal.cuh"
+
+namespace {
+
+constexpr int STATS_THREADS = 128;
+
+struct StatsArgs {
+  const double *obs;
+  int64_t Kp;
+  const int *pose_idx;
+  const long long *row_ptr;
+  const double *coe;
+  const double *fix;  // SoA [10][M] or null
+  int64_t M;
+  const double *poses;
+  int64_t v0, v1;
+  double *stats;      // [v1-v0][20] or null
+  double *res_part;   // [gridDim.x]
+};
+
+template <bool STORE>
+__global__ void __launch_bounds__(STATS_THREADS) voxel_stats_kernel(StatsArgs a) {
+  __shared__ double red[STATS_THREADS / 32][10];
+  __shared__ double tot[10];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double res_acc = 0.0;  // meaningful in warp 0 only (all lanes hold the same value)
+
+  for (int64_t v = a.v0 + blockIdx.x; v < a.v1; v += gridDim.x) {
+    const long long s0 = a.row_ptr[v];
+    const int k = (int)(a.row_ptr[v + 1] - s0);
+    double acc[10];
+#pragma unroll
+    for (int c = 0; c < 10; c++) acc[c] = 0.0;
+    for (int j = tid; j < k; j += STATS_THREADS) {
+      const long long s = s0 + j;
+      double o[10];
+#pragma unroll
+      for (int c = 0; c < 10; c++) o[c] = __ldg(a.obs + c * a.Kp + s);
+      const int pid = __ldg(a.pose_idx + s);
+      double r[9], p[3];
+      load_pose(a.poses + 12 * pid, r, p);
+      const WC w = world_cluster(o, r, p);
+      acc[0] += w.p00; acc[1] += w.p01; acc[2] += w.p02; acc[3] += w.p11; acc[4] += w.p12;
+      acc[5] += w.p22; acc[6] += w.v0;  acc[7] += w.v1;  acc[8] += w.v2;  acc[9] += w.n;
+    }
+#pragma unroll
+    for (int c = 0; c < 10; c++) acc[c] = warp_sum(acc[c]);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 10; c++) red[warp][c] = acc[c];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      if (lane < 10) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < STATS_THREADS / 32; w++) t += red[w][lane];
+        if (a.fix) t += __ldg(a.fix + lane * a.M + v);
+        tot[lane] = t;
+      }
+      __syncwarp();
+      const double NN = tot[9];
+      const double inv = 1.0 / NN;
+      const double vb0 = tot[6] * inv, vb1 = tot[7] * inv, vb2 = tot[8] * inv;
+      double lam[3], u0[3], u1[3], u2[3];
+      eig3_jacobi(tot[0] * inv - vb0 * vb0, tot[1] * inv - vb0 * vb1, tot[2] * inv - vb0 * vb2,
+                  tot[3] * inv - vb1 * vb1, tot[4] * inv - vb1 * vb2, tot[5] * inv - vb2 * vb2, lam, u0, u1, u2);
+      const double coe = __ldg(a.coe + v);
+      res_acc += coe * lam[0];
+      if (STORE && lane == 0) {
+        double *st = a.stats + (v - a.v0) * BALM_STATS_STRIDE;
+        st[0] = vb0; st[1] = vb1; st[2] = vb2;
+        st[3] = u0[0]; st[4] = u0[1]; st[5] = u0[2];
+        st[6] = u1[0]; st[7] = u1[1]; st[8] = u1[2];
+        st[9] = u2[0]; st[10] = u2[1]; st[11] = u2[2];
+        st[12] = inv;
+        st[13] = sqrt(2.0 * coe) * inv;               // sqrt(coe*|w0|), w0 = -2/NN^2 (bavoxel.hpp:385)
+        st[14] = sqrt(2.0 * coe / (lam[1] - lam[0])); // sqrt(coe*|w1|), w1 = 2/(l0-l1) (bavoxel.hpp:392)
+        st[15] = sqrt(2.0 * coe / (lam[2] - lam[0]));
+        st[16] = coe;
+        st[17] = lam[0]; st[18] = lam[1]; st[19] = lam[2];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) a.res_part[blockIdx.x] = res_acc;
+}
+
+// deterministic sum of the per-CTA residual partials (single warp)
+__global__ void residual_reduce_kernel(const double *part, int nparts, double *out, int accumulate) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += 32) s += part[i];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) out[0] = accumulate ? out[0] + s : s;
+}
+
+struct ObsArgs {
+  const double *obs;
+  int64_t Kp;
+  const long long *row_ptr;
+  const double *poses;
+  const double *stats;  // batch-local [nv][20]
+  int64_t v0, v1;       // batch voxel range
+  int N, Np, ldg;
+  int chunk;            // voxels per chunk (dense) or list positions per segment (csc)
+  double *G;            // [3*(v1-v0)][ldg]
+  double *part;         // [chunks][27][Np]
+  // csc
+  const int *csc_ptr, *csc_obs, *csc_vox;
+};
+
+// One lane = one pose; a warp covers 32 consecutive poses and walks a chunk of voxels, so the observation
+// loads of a dense scene (slot j == pose j) are coalesced and the 27 accumulators stay in registers.
+template <bool DENSE>
+__global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile = blockIdx.y * 4 + warp;
+  const int i = tile * 32 + lane;
+  if (tile * 32 >= a.N) return;
+  const bool active = i < a.N;
+  double r[9], p[3];
+  if (active) load_pose(a.poses + 12 * i, r, p);
+  double acc[BALM_ACC];
+#pragma unroll
+  for (int q = 0; q < BALM_ACC; q++) acc[q] = 0.0;
+
+  long long t0, t1;
+  if (DENSE) {
+    t0 = a.v0 + (long long)blockIdx.x * a.chunk;
+    t1 = t0 + a.chunk < a.v1 ? t0 + a.chunk : a.v1;
+  } else {
+    const int b = active ? a.csc_ptr[i] : 0, e = active ? a.csc_ptr[i + 1] : 0;
+    t0 = b + (long long)blockIdx.x * a.chunk;
+    t1 = t0 + a.chunk < e ? t0 + a.chunk : e;
+  }
+
+  for (long long t = t0; t < t1; t++) {
+    long long s, v;
+    if (DENSE) {
+      v = t;
+      s = __ldg(a.row_ptr + v) + i;
+      if (!active) continue;
+    } else {
+      s = a.csc_obs[t];
+      v = a.csc_vox[t];
+    }
+    double o[10];
+#pragma unroll
+    for (int c = 0; c < 10; c++) o[c] = __ldg(a.obs + c * a.Kp + s);
+    const double2 *st2 = reinterpret_cast<const double2 *>(a.stats + (v - a.v0) * BALM_STATS_STRIDE);
+    double st[BALM_STATS_STRIDE];
+#pragma unroll
+    for (int c = 0; c < BALM_STATS_STRIDE / 2; c++) {
+      const double2 x = __ldg(st2 + c);
+      st[2 * c] = x.x;
+      st[2 * c + 1] = x.y;
+    }
+    const WC w = world_cluster(o, r, p);
+    const double *vb = st, *u0 = st + 3, *u1 = st + 6, *u2 = st + 9;
+    const double inv = st[12], coe = st[16];
+    // M_i = [P' - v' vb^T ; (v' - n vb)^T]  (= TC_i * [R_i | p_i - vb]^T, bavoxel.hpp:368-370)
+    const double m00 = w.p00 - w.v0 * vb[0], m01 = w.p01 - w.v0 * vb[1], m02 = w.p02 - w.v0 * vb[2];
+    const double m10 = w.p01 - w.v1 * vb[0], m11 = w.p11 - w.v1 * vb[1], m12 = w.p12 - w.v1 * vb[2];
+    const double m20 = w.p02 - w.v2 * vb[0], m21 = w.p12 - w.v2 * vb[1], m22 = w.p22 - w.v2 * vb[2];
+    const double mb[3] = {w.v0 - w.n * vb[0], w.v1 - w.n * vb[1], w.v2 - w.n * vb[2]};
+    double tk[3][3], sk[3];
+    const double *uu[3] = {u0, u1, u2};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      tk[k][0] = m00 * uu[k][0] + m01 * uu[k][1] + m02 * uu[k][2];
+      tk[k][1] = m10 * uu[k][0] + m11 * uu[k][1] + m12 * uu[k][2];
+      tk[k][2] = m20 * uu[k][0] + m21 * uu[k][1] + m22 * uu[k][2];
+      sk[k] = mb[0] * uu[k][0] + mb[1] * uu[k][1] + mb[2] * uu[k][2];
+    }
+    // g_k^i = (U_k M u_0 + U_0 M u_k)/NN, U_k = [hat(-u_k) 0; 0 u_k]  (bavoxel.hpp:371-378)
+    double gk[3][6];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      double c1[3], c2[3];
+      cross3(uu[k], tk[0], c1);
+      cross3(u0, tk[k], c2);
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        gk[k][q] = -(c1[q] + c2[q]) * inv;
+        gk[k][3 + q] = (uu[k][q] * sk[0] + u0[q] * sk[k]) * inv;
+      }
+    }
+    // a_i = (U_0 TC_i)[:,3] = [-u0 x v' ; n u0]  (bavoxel.hpp:380)
+    const double vw[3] = {w.v0, w.v1, w.v2};
+    double cuv[3];
+    cross3(u0, vw, cuv);
+    const double ai[6] = {-cuv[0], -cuv[1], -cuv[2], w.n * u0[0], w.n * u0[1], w.n * u0[2]};
+
+    // ---- G' rows (3 per voxel), 6 contiguous doubles per pose ----
+    {
+      double *g0 = a.G + (size_t)(3 * (v - a.v0)) * a.ldg + 6 * i;
+      const double c0 = st[13], c1s = st[14], c2s = st[15];
+      double2 *q0 = reinterpret_cast<double2 *>(g0);
+      double2 *q1 = reinterpret_cast<double2 *>(g0 + a.ldg);
+      double2 *q2 = reinterpret_cast<double2 *>(g0 + 2 * (size_t)a.ldg);
+#pragma unroll
+      for (int h = 0; h < 3; h++) {
+        q0[h] = make_double2(c0 * ai[2 * h], c0 * ai[2 * h + 1]);
+        q1[h] = make_double2(c1s * gk[1][2 * h], c1s * gk[1][2 * h + 1]);
+        q2[h] = make_double2(c2s * gk[2][2 * h], c2s * gk[2][2 * h + 1]);
+      }
+    }
+    // ---- gradient (bavoxel.hpp:381) ----
+#pragma unroll
+    for (int q = 0; q < 6; q++) acc[q] += coe * gk[0][q];
+    // ---- diagonal block: coe*( 2/NN * U0 TCT U0^T + [[Ell+Ell^T,0],[0,0]] )  (bavoxel.hpp:387-388,397-402) ----
+    {
+      const double f = 2.0 * inv * coe;
+      // X = hat(u0) * P'
+      const double Pw[3][3] = {{w.p00, w.p01, w.p02}, {w.p01, w.p11, w.p12}, {w.p02, w.p12, w.p22}};
+      double X[3][3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const double col[3] = {Pw[0][c], Pw[1][c], Pw[2][c]};
+        double xc[3];
+        cross3(u0, col, xc);
+        X[0][c] = xc[0]; X[1][c] = xc[1]; X[2][c] = xc[2];
+      }
+      // TL = X * hat(u0)^T : row r = u0 x X[r,:]
+      double TL[3][3];
+#pragma unroll
+      for (int rr = 0; rr < 3; rr++) cross3(u0, X[rr], TL[rr]);
+      // Ell + Ell^T = (u0 t0^T + t0 u0^T - 2 (t0.u0) I)/NN with t0 = M[0:3,:] u0
+      const double *t0v = tk[0];
+      const double tu = t0v[0] * u0[0] + t0v[1] * u0[1] + t0v[2] * u0[2];
+      const double fe = coe * inv;
+      int q = 6;
+#pragma unroll
+      for (int rr = 0; rr < 6; rr++) {
+#pragma unroll
+        for (int cc = rr; cc < 6; cc++) {
+          double val;
+          if (rr < 3 && cc < 3) {
+            val = f * TL[rr][cc] + fe * (u0[rr] * t0v[cc] + t0v[rr] * u0[cc] - (rr == cc ? 2.0 * tu : 0.0));
+          } else if (rr < 3) {
+            val = f * (-cuv[rr] * u0[cc - 3]);
+          } else {
+            val = f * w.n * u0[rr - 3] * u0[cc - 3];
+          }
+          acc[q++] += val;
+        }
+      }
+    }
+  }
+  if (active) {
+    double *pp = a.part + (size_t)blockIdx.x * BALM_ACC * a.Np + i;
+#pragma unroll
+    for (int q = 0; q < BALM_ACC; q++) pp[(size_t)q * a.Np] = acc[q];
+  }
+}
+
+__global__ void obs_reduce_kernel(const double *part, int chunks, int total, double *accum, int add) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  double s = 0.0;
+  for (int c = 0; c < chunks; c++) s += part[(size_t)c * total + e];
+  accum[e] = add ? accum[e] + s : s;
+}
+
+}  // namespace
+
+int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool store_stats, bool use_fix,
+                       double *residual_out_dev) {
+  // residual_out_dev: accumulated (+=) when it is not the first batch -> caller zeroes it first
+  const int64_t nv = v1 - v0;
+  if (nv <= 0) return BALM_OK;
+  int blocks = (int)(nv < (int64_t)c->res_blocks ? nv : c->res_blocks);
+  StatsArgs a{c->obs, c->Kp, c->pose_idx, c->row_ptr, c->coe, use_fix ? c->fix : nullptr, c->M, poses, v0, v1,
+              store_stats ? c->stats : nullptr, c->res_part};
+  if (store_stats) voxel_stats_kernel<true><<<blocks, STATS_THREADS, 0, c->stream>>>(a);
+  else voxel_stats_kernel<false><<<blocks, STATS_THREADS, 0, c->stream>>>(a);
+  residual_reduce_kernel<<<1, 32, 0, c->stream>>>(c->res_part, blocks, residual_out_dev, 1);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return BALM_OK;
+}
+
+int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch) {
+  const int64_t nv = v1 - v0;
+  if (nv <= 0) return BALM_OK;
+  const int tiles = (c->N + 31) / 32;
+  ObsArgs a{};
+  a.obs = c->obs; a.Kp = c->Kp; a.row_ptr = c->row_ptr; a.poses = poses; a.stats = c->stats;
+  a.v0 = v0; a.v1 = v1; a.N = c->N; a.Np = c->Np; a.ldg = c->ldg; a.G = c->G; a.part = c->obs_part;
+  a.csc_ptr = c->csc_ptr; a.csc_obs = c->csc_obs; a.csc_vox = c->csc_vox;
+  int chunks;
+  if (c->dense) {
+    chunks = (int)(nv < (int64_t)c->obs_chunks ? nv : c->obs_chunks);
+    a.chunk = (int)((nv + chunks - 1) / chunks);
+    chunks = (int)((nv + a.chunk - 1) / a.chunk);
+  } else {
+    // sparse: G' rows of non-observing poses must be zero
+    CUDA_TRY(cudaMemsetAsync(c->G, 0, sizeof(double) * (size_t)3 * nv * c->ldg, c->stream));
+    const int len = c->csc_max_len > 0 ? c->csc_max_len : 1;
+    chunks = len < c->obs_chunks ? len : c->obs_chunks;
+    a.chunk = (len + chunks - 1) / chunks;
+    chunks = (len + a.chunk - 1) / a.chunk;
+  }
+  dim3 grid(chunks, (tiles + 3) / 4);
+  if (c->dense) obs_pass_kernel<true><<<grid, 128, 0, c->stream>>>(a);
+  else obs_pass_kernel<false><<<grid, 128, 0, c->stream>>>(a);
+  const int total = BALM_ACC * c->Np;
+  obs_reduce_kernel<<<(total + 255) / 256, 256, 0, c->stream>>>(c->obs_part, chunks, total, c->accum,
+                                                                first_batch ? 0 : 1);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return BALM_OK;
+}

@@ -1,0 +1,136 @@
+/*
+ * balm_b200.h -- C ABI of libbalm_b200.so: the B200-native replacement for the inner optimisation loop of
+ * BALM 2.0 (VOX_HESS factor evaluation + BALM2::damping_iter()).
+ *
+ * The reference has no FFI/plugin interface: its seam is the header-level C++ API of
+ * /root/reference/src/benchmark/bavoxel.hpp.  Every entry point below names the reference interface it
+ * replaces (file:line relative to /root/reference).  include/bavoxel_b200.hpp is the C++ shim that keeps the
+ * reference's class/method names on top of this ABI; balm_b200/ (Python) mirrors the same names via ctypes.
+ * INTEGRATION.md shows the binding a BALM maintainer adds.
+ *
+ * Conventions (same as the reference):
+ *   poses12 : N x 12 doubles; per pose R column-major (Eigen default) then p    -- IMUST::R, IMUST::p
+ *                                                                    (include/tools.hpp:141-201)
+ *   obs10   : K x 10 doubles; per (voxel,pose) observation P00,P01,P02,P11,P12,P22,v0,v1,v2,N
+ *                                                      -- PointCluster{P,v,N} (include/tools.hpp:290-349)
+ *   row_ptr : M+1 int64 CSR offsets voxel -> observations; pose_idx : K int32, ascending inside a voxel.
+ *             A slot is present iff PointCluster::N != 0 (bavoxel.hpp:34,332).
+ *   coe     : M doubles, push_voxel weight (bavoxel.hpp:42-48)
+ *   fix10   : M x 10 doubles or NULL, the fixed / marginalised cluster sig_vecs[a] (bavoxel.hpp:47,441)
+ *   H       : n x n doubles, column-major, full symmetric, n = 6N; block (i,j) at rows 6i.., cols 6j..
+ *             (bavoxel.hpp:394,416); g : n; unknown order per pose [phi(3), dt(3)] (DVEL = 6, tools.hpp:20)
+ * All pointers are HOST pointers unless the name ends in _dev.  No torch/Eigen types cross this boundary.
+ * A context owns one CUDA stream and is not re-entrant; distinct contexts are independent.
+ */
+#ifndef BALM_B200_H
+#define BALM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct balm_ctx balm_ctx;
+
+typedef enum {
+  BALM_OK = 0,
+  BALM_ERR_INVALID = 1,        /* bad argument / call order */
+  BALM_ERR_CUDA = 2,           /* CUDA runtime error, see balm_last_error() */
+  BALM_ERR_NOT_PD = 3,         /* (H + u D) had a zero/tiny pivot; LM treats it as a rejected step */
+  BALM_ERR_TOO_FEW_PLANES = 4, /* reference prints + exit(0) (bavoxel.hpp:1079-1085) */
+  BALM_ERR_NCCL = 5,
+  BALM_ERR_UNSUPPORTED = 6
+} balm_status;
+
+/* Arithmetic of the rank-3M Hessian accumulation  H -= G' G'^T  (bavoxel.hpp:385,392,410-416). */
+typedef enum {
+  BALM_PREC_FP64 = 0,   /* fp64 DMMA accumulation (BASELINE config C2, "fp64 accumulation") */
+  BALM_PREC_TENSOR = 1  /* tcgen05 int8 split-integer (Ozaki) accumulation, exact int32 sums, fp64 result */
+} balm_precision;
+
+typedef struct {
+  int max_iter;             /* 10  (bavoxel.hpp:1104); benchmark_virtual twin: 20 (benchmark_virtual.cpp:408) */
+  double u0;                /* 0.01 (bavoxel.hpp:1087); twin: 0.1 (benchmark_virtual.cpp:380) */
+  double v0;                /* 2 */
+  double rel_tol;           /* 1e-6 (bavoxel.hpp:1155); < 0 disables the convergence exit (timing runs) */
+  int hess_includes_fix;    /* 0: bavoxel.hpp:325 (fix ignored in H,g); 1: benchmark_virtual.cpp:241-243 */
+  int gauge_mode;           /* 0: bavoxel.hpp:1159-1164; 1: benchmark_virtual.cpp:472-479; 2: none */
+  int min_planes_per_pose;  /* 20 (bavoxel.hpp:1079); 0 disables the precheck */
+  int verbose;              /* 1: print the reference's per-iteration line (bavoxel.hpp:1132) */
+} balm_lm_opts;
+
+typedef struct {
+  double r1, r2, u, v, q, q1; /* exactly the values printed at bavoxel.hpp:1132 */
+  int accepted;
+  int recomputed_hess;
+  int not_pd;
+} balm_trace;
+
+/* Per-phase device timings of the last balm_damping_iter / balm_evaluate (CUDA events on the ctx stream). */
+typedef struct {
+  float ms_stats, ms_obs, ms_slice, ms_syrk, ms_assemble, ms_allreduce, ms_solve, ms_residual, ms_update;
+  int launches; /* kernels launched by the library since balm_reset_counters() */
+} balm_timings;
+
+const char *balm_last_error(void);
+int balm_version(void);
+
+/* ctx lifetime. `device` is the CUDA ordinal. Replaces constructing VOX_HESS + BALM2 (bavoxel.hpp:21,984). */
+int balm_create(balm_ctx **out, int n_poses, int device, int precision);
+int balm_destroy(balm_ctx *ctx);
+
+/* Registers all plane voxels at once = the sequence of VOX_HESS::push_voxel calls (bavoxel.hpp:30-51) made by
+ * OCTO_TREE_NODE::tras_opt (bavoxel.hpp:908-929). Host arrays are copied (H2D) and may be freed on return. */
+int balm_set_voxels(balm_ctx *ctx, int64_t n_voxels, const int64_t *row_ptr, const int32_t *pose_idx,
+                    const double *obs10, const double *fix10, const double *coe);
+/* Same, but the arrays already live in device memory of ctx's GPU (used for HBM-resident timing). */
+int balm_set_voxels_dev(balm_ctx *ctx, int64_t n_voxels, const int64_t *row_ptr_dev, const int32_t *pose_idx_dev,
+                        const double *obs10_dev, const double *fix10_dev, const double *coe_dev, int64_t n_obs);
+
+/* VOX_HESS::left_evaluate_acc2(xs, head, end, Hess, JacT, residual) (bavoxel.hpp:304-426).
+ * H (n*n) and g (n) may be NULL to keep the result on the device only. With a communicator attached
+ * (balm_comm_init) the result is the all-reduced sum over ranks = divide_thread_left's reduction
+ * (bavoxel.hpp:1049-1056). head/end select a voxel range of THIS rank's voxels ([0,M) = all). */
+int balm_evaluate(balm_ctx *ctx, const double *poses12, int64_t head, int64_t end, int include_fix, double *H,
+                  double *g, double *residual);
+/* VOX_HESS::evaluate_only_residual(xs, residual) (bavoxel.hpp:428-470) */
+int balm_residual(balm_ctx *ctx, const double *poses12, double *residual);
+/* D = diag(H); dx = (H + u D)^-1 (-g); q1 = 0.5 dx.(u D dx - g) on the H,g of the last balm_evaluate
+ * (bavoxel.hpp:1113-1114,1127). not_pd set when the LDL^T met a zero/tiny pivot. dx (n) may be NULL. */
+int balm_solve(balm_ctx *ctx, double u, double *dx, double *q1, int *not_pd);
+/* BALM2::damping_iter(x_stats, voxhess) (bavoxel.hpp:1069-1166). poses12 updated in place.
+ * trace: room for opts->max_iter entries (may be NULL). poses_per_iter: max_iter*N*12 doubles or NULL,
+ * receives the accepted pose set after every iteration (before the gauge step) for parity checks. */
+int balm_damping_iter(balm_ctx *ctx, double *poses12, const balm_lm_opts *opts, balm_trace *trace, int *n_iters,
+                      double *poses_per_iter);
+void balm_default_lm_opts(balm_lm_opts *opts);
+
+/* Multi-GPU: voxels are sharded across ranks by the caller (each rank registers its own shard); the library
+ * all-reduces [H | g | r] with NCCL after every evaluation and the scalar after every residual pass.
+ * unique_id: 128 bytes from balm_comm_unique_id() on rank 0, broadcast by the caller (torch.distributed, MPI). */
+int balm_comm_unique_id(void *out128);
+int balm_comm_init(balm_ctx *ctx, int rank, int world, const void *unique_id128);
+
+/* Instrumentation */
+int balm_get_timings(balm_ctx *ctx, balm_timings *out);
+int balm_reset_counters(balm_ctx *ctx);
+int balm_sync(balm_ctx *ctx);
+/* Device pointers of the last evaluation's H (n*n col-major), g (n) -- for zero-copy consumers. */
+int balm_device_views(balm_ctx *ctx, double **H_dev, double **g_dev);
+
+/* Synthetic scene of the benchmark_virtual shape generated directly in HBM
+ * (benchmark_virtual.cpp:547-606 scene, :491-503 pose noise, :391 coe): every pose sees every plane,
+ * pts_size points per observation. Outputs are device buffers owned by the ctx and registered as its voxels;
+ * poses_gt / poses_init (N*12 host doubles) receive ground truth and perturbed start. first_voxel offsets the
+ * plane ids so ranks generate disjoint shards of one global scene. */
+int balm_synth_virtual(balm_ctx *ctx, int64_t n_voxels, int64_t first_voxel, int pts_size, double point_noise,
+                       double surf_range, uint64_t seed, double *poses_gt, double *poses_init);
+/* Copies the registered voxels back to host arrays (K*10, K, M+1, M) -- lets tests/bench feed the oracle and
+ * the host-buffer (e2e) path with the very scene generated above. Any pointer may be NULL. */
+int balm_download_voxels(balm_ctx *ctx, int64_t *row_ptr, int32_t *pose_idx, double *obs10, double *coe);
+int64_t balm_num_obs(balm_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
