@@ -13,7 +13,7 @@ PREC_FP64, PREC_TENSOR = 0, 1
 class LmOpts(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("u0", C.c_double), ("v0", C.c_double), ("rel_tol", C.c_double),
                 ("hess_includes_fix", C.c_int), ("gauge_mode", C.c_int), ("min_planes_per_pose", C.c_int),
-                ("verbose", C.c_int)]
+                ("verbose", C.c_int), ("force_hess", C.c_int)]
 
 
 class Trace(C.Structure):
@@ -39,7 +39,7 @@ _lib = None
 SYMBOLS = ["balm_last_error", "balm_version", "balm_create", "balm_destroy", "balm_set_voxels",
            "balm_set_voxels_dev", "balm_evaluate", "balm_residual", "balm_solve", "balm_damping_iter",
            "balm_default_lm_opts", "balm_comm_unique_id", "balm_comm_init", "balm_get_timings",
-           "balm_reset_counters", "balm_sync", "balm_device_views", "balm_synth_virtual",
+           "balm_reset_counters", "balm_sync", "balm_timer_begin", "balm_timer_end", "balm_device_views", "balm_synth_virtual",
            "balm_download_voxels", "balm_num_obs"]
 
 
@@ -69,6 +69,8 @@ def lib():
         L.balm_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
         L.balm_reset_counters.argtypes = [C.c_void_p]
         L.balm_sync.argtypes = [C.c_void_p]
+        L.balm_timer_begin.argtypes = [C.c_void_p]
+        L.balm_timer_end.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.balm_device_views.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.balm_synth_virtual.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double,
                                          C.c_uint64, C.c_void_p, C.c_void_p]

@@ -81,10 +81,10 @@ class Context:
         return dx, q1.value, bool(bad.value)
 
     def damping_iter(self, poses12, max_iter=10, u0=0.01, v0=2.0, rel_tol=1e-6, hess_includes_fix=False,
-                     gauge_mode=0, min_planes_per_pose=20, verbose=False, want_per_iter=False):
+                     gauge_mode=0, min_planes_per_pose=20, verbose=False, want_per_iter=False, force_hess=False):
         poses = np.array(poses12, dtype=np.float64, order="C", copy=True)
         opts = L.LmOpts(max_iter, u0, v0, rel_tol, int(hess_includes_fix), gauge_mode, min_planes_per_pose,
-                        int(verbose))
+                        int(verbose), int(force_hess))
         trace = (L.Trace * max_iter)()
         n_it = C.c_int()
         per_iter = np.zeros((max_iter, self.N, 12)) if want_per_iter else None
@@ -112,6 +112,14 @@ class Context:
 
     def reset_counters(self):
         L.check(L.lib().balm_reset_counters(self._h))
+
+    def timer_begin(self):
+        L.check(L.lib().balm_timer_begin(self._h))
+
+    def timer_end(self):
+        ms = C.c_float()
+        L.check(L.lib().balm_timer_end(self._h, C.byref(ms)))
+        return ms.value
 
     def sync(self):
         L.check(L.lib().balm_sync(self._h))

@@ -365,6 +365,7 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
   bool first = true;
   if (head == end) {  // empty range: H = 0
     CUDA_TRY(cudaMemsetAsync(c->H, 0, sizeof(double) * ((size_t)c->n * c->n + c->n + 1), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->scal, 0, sizeof(double), c->stream));
     return BALM_OK;
   }
   for (int64_t v0 = head; v0 < end; v0 += c->VB) {
@@ -463,7 +464,7 @@ extern "C" int balm_solve(balm_ctx *c, double u, double *dx, double *q1, int *no
 
 extern "C" void balm_default_lm_opts(balm_lm_opts *o) {
   o->max_iter = 10; o->u0 = 0.01; o->v0 = 2; o->rel_tol = 1e-6; o->hess_includes_fix = 0; o->gauge_mode = 0;
-  o->min_planes_per_pose = 20; o->verbose = 0;
+  o->min_planes_per_pose = 20; o->verbose = 0; o->force_hess = 0;
 }
 
 extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opts *o, balm_trace *trace, int *n_iters,
@@ -515,7 +516,7 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
     } else {  // bavoxel.hpp:1144-1149
       u = u * v;
       v = 2 * v;
-      calc_hess = false;
+      calc_hess = o->force_hess != 0;
     }
     if (trace) trace[it] = t;
     if (poses_per_iter)
@@ -574,6 +575,23 @@ extern "C" int balm_sync(balm_ctx *c) {
   if (!c) return BALM_ERR_INVALID;
   CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return BALM_OK;
+}
+extern "C" int balm_timer_begin(balm_ctx *c) {
+  if (!c) return BALM_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaEventRecord(c->ev[11], c->stream));
+  return BALM_OK;
+}
+extern "C" int balm_timer_end(balm_ctx *c, float *ms) {
+  if (!c || !ms) return BALM_ERR_INVALID;
+  cudaEvent_t e;
+  CUDA_TRY(cudaEventCreate(&e));
+  CUDA_TRY(cudaEventRecord(e, c->stream));
+  CUDA_TRY(cudaEventSynchronize(e));
+  CUDA_TRY(cudaEventElapsedTime(ms, c->ev[11], e));
+  cudaEventDestroy(e);
   return BALM_OK;
 }
 extern "C" int balm_device_views(balm_ctx *c, double **H_dev, double **g_dev) {

@@ -57,6 +57,8 @@ typedef struct {
   int gauge_mode;           /* 0: bavoxel.hpp:1159-1164; 1: benchmark_virtual.cpp:472-479; 2: none */
   int min_planes_per_pose;  /* 20 (bavoxel.hpp:1079); 0 disables the precheck */
   int verbose;              /* 1: print the reference's per-iteration line (bavoxel.hpp:1132) */
+  int force_hess;           /* 1: re-evaluate H,g every iteration even after a rejected step (benchmarks: makes
+                               every LM iteration the same amount of work; the reference reuses H, :1148) */
 } balm_lm_opts;
 
 typedef struct {
@@ -115,6 +117,9 @@ int balm_comm_init(balm_ctx *ctx, int rank, int world, const void *unique_id128)
 int balm_get_timings(balm_ctx *ctx, balm_timings *out);
 int balm_reset_counters(balm_ctx *ctx);
 int balm_sync(balm_ctx *ctx);
+/* CUDA-event bracket on the ctx stream: begin records, end records + synchronises and returns elapsed ms. */
+int balm_timer_begin(balm_ctx *ctx);
+int balm_timer_end(balm_ctx *ctx, float *ms);
 /* Device pointers of the last evaluation's H (n*n col-major), g (n) -- for zero-copy consumers. */
 int balm_device_views(balm_ctx *ctx, double **H_dev, double **g_dev);
 

@@ -22,10 +22,10 @@ def _oracle(sc):
     return orc.Oracle(sc["n_poses"], sc["row_ptr"], sc["pose_idx"], sc["obs10"], sc["coe"], sc["fix10"])
 
 
-def _check_eval(c, o, poses, include_fix=False, head=0, end=None, tolH=1e-9):
+def _check_eval(c, o, poses, include_fix=False, head=0, end=None, tolH=1e-9, tolr=1e-12):
     H, g, r = c.evaluate(poses, head, end, include_fix=include_fix)
     Ho, go, ro = o.evaluate(poses, head, end, include_fix=include_fix)
-    assert abs(r - ro) <= 1e-12 * abs(ro), (r, ro)
+    assert abs(r - ro) <= tolr * abs(ro), (r, ro)
     assert np.abs(g - go).max() <= 1e-10 * np.abs(go).max()
     assert np.abs(H - Ho).max() <= tolH * np.abs(Ho).max()
     assert np.array_equal(H, H.T)
@@ -56,8 +56,9 @@ def test_evaluate_matches_oracle(n_poses, n_planes, drop, with_fix):
     r = c.residual(sc["poses_init"])
     ro = o.residual(sc["poses_init"])
     assert abs(r - ro) <= 1e-12 * abs(ro)
-    # at the ground truth as well (different conditioning: lambda_min at the noise floor)
-    _check_eval(c, o, sc["poses_gt"])
+    # at the ground truth as well: lambda_min sits at the noise floor (1e-4) of a covariance whose raw second
+    # moments are O(10), so ANY fp64 evaluation (the oracle included) carries eps*|P/N|/lambda_min ~ 1e-11
+    _check_eval(c, o, sc["poses_gt"], tolr=1e-10)
 
 
 def test_voxel_range_semantics():
