@@ -361,7 +361,6 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
   double *r_dev = c->g + c->n;  // contiguous with H and g -> one all-reduce
   CUDA_TRY(cudaMemsetAsync(r_dev, 0, sizeof(double), c->stream));
   float ms;
-  c->tm.ms_stats = c->tm.ms_obs = c->tm.ms_syrk = c->tm.ms_slice = 0;
   bool first = true;
   if (head == end) {  // empty range: H = 0
     CUDA_TRY(cudaMemsetAsync(c->H, 0, sizeof(double) * ((size_t)c->n * c->n + c->n + 1), c->stream));
@@ -391,8 +390,9 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
   CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->scal, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_TRY(cudaEventSynchronize(c->ev[6]));
-  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->tm.ms_assemble = ms;
-  cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); c->tm.ms_allreduce = ms;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->tm.ms_assemble += ms;
+  cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); c->tm.ms_allreduce += ms;
+  c->tm.n_eval += 1;
   return BALM_OK;
 }
 
@@ -408,7 +408,8 @@ static int residual_dev(balm_ctx *c, const double *poses, double *host_out) {
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   float ms;
   cudaEventElapsedTime(&ms, c->ev[7], c->ev[8]);
-  c->tm.ms_residual = ms;
+  c->tm.ms_residual += ms;
+  c->tm.n_residual += 1;
   *host_out = c->h_scal[2];
   return BALM_OK;
 }
@@ -444,7 +445,8 @@ static int solve_dev(balm_ctx *c, double u, double *q1, int *not_pd) {
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   float ms;
   cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]);
-  c->tm.ms_solve = ms;
+  c->tm.ms_solve += ms;
+  c->tm.n_solve += 1;
   *q1 = c->h_scal[1];
   *not_pd = c->h_flags[0] != 0 || !std::isfinite(*q1);
   return BALM_OK;
@@ -527,7 +529,7 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
   if (o->gauge_mode == 0 || o->gauge_mode == 1) TRY(launch_gauge(c, c->poses, o->gauge_mode));
   CUDA_TRY(cudaMemcpyAsync(poses12, c->poses, pbytes, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  c->tm.ms_update = ms_update;
+  (void)ms_update;
   return BALM_OK;
 }
 
@@ -569,6 +571,7 @@ extern "C" int balm_get_timings(balm_ctx *c, balm_timings *out) {
 extern "C" int balm_reset_counters(balm_ctx *c) {
   if (!c) return BALM_ERR_INVALID;
   c->launches = 0;
+  c->tm = balm_timings{};
   return BALM_OK;
 }
 extern "C" int balm_sync(balm_ctx *c) {

@@ -68,10 +68,12 @@ typedef struct {
   int not_pd;
 } balm_trace;
 
-/* Per-phase device timings of the last balm_damping_iter / balm_evaluate (CUDA events on the ctx stream). */
+/* Per-phase device time (CUDA events on the ctx stream), SUMMED since balm_reset_counters(), with the
+ * number of evaluations / solves / residual passes that contributed and the kernels launched. */
 typedef struct {
   float ms_stats, ms_obs, ms_slice, ms_syrk, ms_assemble, ms_allreduce, ms_solve, ms_residual, ms_update;
-  int launches; /* kernels launched by the library since balm_reset_counters() */
+  int launches;   /* kernels launched by the library since balm_reset_counters() */
+  int n_eval, n_solve, n_residual;
 } balm_timings;
 
 const char *balm_last_error(void);
