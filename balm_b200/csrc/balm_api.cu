@@ -372,6 +372,7 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     TRY(launch_voxel_stats(c, poses, v0, v1, true, include_fix, r_dev));
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if (c->prec == BALM_PREC_TENSOR) TRY(tensor_syrk_prepare(c));
     TRY(launch_obs_pass(c, poses, v0, v1, first));
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     if (c->prec == BALM_PREC_TENSOR) TRY(launch_tensor_syrk(c, 3 * (v1 - v0), first));
@@ -380,7 +381,13 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
     CUDA_TRY(cudaEventSynchronize(c->ev[3]));
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->tm.ms_stats += ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->tm.ms_obs += ms;
-    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->tm.ms_syrk += ms;
+    if (c->prec == BALM_PREC_TENSOR) {
+      cudaEventElapsedTime(&ms, c->ev[2], c->ev[12]); c->tm.ms_slice += ms;
+      cudaEventElapsedTime(&ms, c->ev[12], c->ev[3]); c->tm.ms_syrk += ms;
+      TRY(tensor_syrk_check(c));
+    } else {
+      cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->tm.ms_syrk += ms;
+    }
     first = false;
   }
   CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));

@@ -118,6 +118,7 @@ struct ObsArgs {
   int chunk;            // voxels per chunk (dense) or list positions per segment (csc)
   double *G;            // [3*(v1-v0)][ldg]
   double *part;         // [chunks][27][Np]
+  unsigned long long *colmax;  // [ldg] or null: running max |G'[:,j]| (tensor path column scales)
   // csc
   const int *csc_ptr, *csc_obs, *csc_vox;
 };
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
   double acc[BALM_ACC];
 #pragma unroll
   for (int q = 0; q < BALM_ACC; q++) acc[q] = 0.0;
+  double cmax[6] = {0, 0, 0, 0, 0, 0};
 
   long long t0, t1;
   if (DENSE) {
@@ -217,6 +219,9 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
         q1[h] = make_double2(c1s * gk[1][2 * h], c1s * gk[1][2 * h + 1]);
         q2[h] = make_double2(c2s * gk[2][2 * h], c2s * gk[2][2 * h + 1]);
       }
+#pragma unroll
+      for (int q = 0; q < 6; q++)
+        cmax[q] = fmax(cmax[q], fmax(fabs(c0 * ai[q]), fmax(fabs(c1s * gk[1][q]), fabs(c2s * gk[2][q]))));
     }
     // ---- gradient (bavoxel.hpp:381) ----
 #pragma unroll
@@ -260,6 +265,11 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
       }
     }
   }
+  if (active && a.colmax) {
+#pragma unroll
+    for (int q = 0; q < 6; q++)  // non-negative doubles order like their bit patterns
+      atomicMax(a.colmax + 6 * i + q, (unsigned long long)__double_as_longlong(cmax[q]));
+  }
   if (active) {
     double *pp = a.part + (size_t)blockIdx.x * BALM_ACC * a.Np + i;
 #pragma unroll
@@ -301,6 +311,7 @@ int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bo
   a.obs = c->obs; a.Kp = c->Kp; a.row_ptr = c->row_ptr; a.poses = poses; a.stats = c->stats;
   a.v0 = v0; a.v1 = v1; a.N = c->N; a.Np = c->Np; a.ldg = c->ldg; a.G = c->G; a.part = c->obs_part;
   a.csc_ptr = c->csc_ptr; a.csc_obs = c->csc_obs; a.csc_vox = c->csc_vox;
+  a.colmax = c->colmax;
   int chunks;
   if (c->dense) {
     chunks = (int)(nv < (int64_t)c->obs_chunks ? nv : c->obs_chunks);

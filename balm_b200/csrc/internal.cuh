@@ -71,7 +71,7 @@ struct balm_ctx {
   // ---- tensor path (int8 split-integer) ----
   int slices = 6;
   int8_t *Gq = nullptr;           // [slices][3*VBp][ldq] int8
-  int *row_exp = nullptr;         // [n] per-row exponent
+  unsigned long long *colmax = nullptr;  // [ldg] bit patterns of max |G'[:,j]| of the current batch
   void *tmap = nullptr;           // CUtensorMap storage
 
   // ---- multi-GPU ----
@@ -81,7 +81,7 @@ struct balm_ctx {
 
   // ---- instrumentation ----
   balm_timings tm{};
-  cudaEvent_t ev[12] = {};
+  cudaEvent_t ev[16] = {};
   long long launches = 0;
 };
 
@@ -226,3 +226,5 @@ int launch_synth(balm_ctx *c, int64_t n_voxels, int64_t first_voxel, int pts, do
 int tensor_syrk_init(balm_ctx *c);
 int launch_tensor_syrk(balm_ctx *c, int64_t rows, bool first_batch);
 void tensor_syrk_free(balm_ctx *c);
+int tensor_syrk_prepare(balm_ctx *c);
+int tensor_syrk_check(balm_ctx *c);

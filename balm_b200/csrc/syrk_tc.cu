@@ -1,13 +1,470 @@
-// syrk_tc.cu -- tcgen05 (5th-gen tensor core) path of the rank-3M symmetric update. Placeholder until the
-// split-integer kernel lands: BALM_PREC_TENSOR contexts fail loudly instead of silently falling back.
+// syrk_tc.cu -- tcgen05 (5th-gen tensor core) path of the rank-3M symmetric update S = G'^T G' (kernel K4).
+//
+// tcgen05 has no fp64 MMA kind, so the fp64 product is computed EXACTLY in integers (Ozaki-style split):
+//   per column j of G' (= one pose DOF) a power-of-two scale sc_j = 2^p_j with |G'[c][j]| * sc_j < 2^(8S-2);
+//   X[c][j] = rint(G'[c][j] * sc_j) is split into S balanced base-256 digits q_s in [-128,127] (int8 planes);
+//   T_d = sum_{s+t=d} sum_c q_s[c][i] * q_t[c][j]  accumulates in int32 TMEM accumulators with NO rounding
+//   (kind::i8, |product| <= 2^14, at most S*rows < 2^17 terms per accumulator -> |T_d| < 2^31);
+//   S_ij = (256^(S-1)/sc_i)(256^(S-1)/sc_j) * sum_{d<S} 256^-d T_d   evaluated in fp64 by the epilogue.
+// The only approximation is the fixed-point rounding of G' to 8S-2 = 30 bits below each column's maximum
+// (S = 4) and the dropped digit pairs s+t >= S (same order); integer accumulation is associative, so the
+// result does not depend on tile order, k-splits or the number of GPUs.
+//
+// Kernel anatomy (one CTA per SM, persistent over (tile, k-split) items, 192 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor.3d of the S int8 planes of the A (rows bi) and B (rows bj)
+//              128-column blocks, 128B-swizzled, into a 3-stage shared-memory ring (mbarrier full/empty)
+//   warp 1   : MMA issuer    -- one elected lane issues tcgen05.mma.cta_group::1.kind::i8, M=128 N=128 K=32,
+//              both operands MN-major (pose index contiguous), S(S+1)/2 = 10 digit-pair products per K step
+//              into S accumulators (S*128 = 512 TMEM columns); tcgen05.commit releases the smem stage
+//   warps 2-5: epilogue      -- tcgen05.ld 32x32b of the S accumulators, fp64 Horner combine, column scales,
+//              fp64 partial tile to global (same partial layout as the fp64 path -> same assemble kernel)
+#include <cuda.h>
 #include "internal.cuh"
 
+namespace {
+
+constexpr int TILE = BALM_SYRK_TILE;  // 128
+constexpr int SMAX = 4;               // digit planes (TMEM: SMAX * 128 columns = 512)
+constexpr int KS = 64;                // contraction rows per pipeline stage
+constexpr int UMMA_K = 32;            // int8
+constexpr int STAGES = 3;
+constexpr int PLANE_TILE_BYTES = KS * TILE;             // 8192: one plane, one operand, one stage
+constexpr int STAGE_BYTES = 2 * SMAX * PLANE_TILE_BYTES;  // 65536
+constexpr int TC_THREADS = 192;
+constexpr int MAX_ROWS_PER_ITEM = 32768 - KS;           // S * rows * 2^14 < 2^31
+
+// ---------------- PTX wrappers ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a pipeline bug must not hang the GPU box. On timeout set the error flag and bail out.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *err) {
+  const uint32_t a = smem_u32(bar);
+  for (long long it = 0; it < (1ll << 22); it++) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return true;
+    if ((it & 1023) == 1023 && *((volatile int *)err) != 0) return false;
+  }
+  atomicExch(err, 2);
+  return false;
+}
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// UMMA shared-memory descriptor, MN-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   canonical layout (16-byte units) Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)):
+//   128 contiguous bytes along MN per k row, 8 k rows per 1024-byte swizzle atom, SBO = next group of 8 k rows,
+//   LBO = next 128-byte block along MN (unused: M = N = 128 int8 = one block).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);           // start address  [0,14)
+  d |= (uint64_t)((PLANE_TILE_BYTES >> 4) & 0x3FFF) << 16;  // LBO            [16,30)
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;           // SBO            [32,46)
+  d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): S32 accumulate, signed int8 A and B, both MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcArgs {
+  int64_t rows;       // contraction rows of this batch (3 per voxel)
+  int nb, tiles, splits, S;
+  const double *isc;  // [ldq]  256^(S-1) / sc_j
+  double *part;       // [splits][tiles][128*128]
+  int accumulate;
+  int *err;
+};
+
+__device__ __forceinline__ void tile_coords_tc(int t, int nb, int &bi, int &bj) {
+  int r = 0, rem = t;
+  while (rem >= nb - r) { rem -= nb - r; r++; }
+  bi = r;
+  bj = r + rem;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte aligned stage ring, then barriers
+  uint8_t *stage_base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_base + STAGES * STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tmem_full = empty_bar + STAGES;
+  uint64_t *tmem_empty = tmem_full + 1;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.S;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_ptr)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_items = a.tiles * a.splits;
+  const int64_t per = ((a.rows + a.splits - 1) / a.splits + KS - 1) / KS * KS;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
+      uint32_t it = 0;
+      bool alive = true;
+      for (int item = blockIdx.x; alive && item < n_items; item += gridDim.x) {
+        const int t = item % a.tiles, sp = item / a.tiles;
+        int bi, bj;
+        tile_coords_tc(t, a.nb, bi, bj);
+        const int64_t k_begin = (int64_t)sp * per;
+        int64_t k_end = k_begin + per;
+        if (k_end > a.rows) k_end = a.rows;
+        const int nsteps = k_end > k_begin ? (int)((k_end - k_begin + KS - 1) / KS) : 0;
+        const bool diag = (bi == bj);
+        for (int ks = 0; ks < nsteps; ks++, it++) {
+          const int st = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          if (!mbar_wait(&empty_bar[st], ph ^ 1, a.err)) { alive = false; break; }
+          uint8_t *sb = stage_base + st * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[st], (diag ? 1 : 2) * S * PLANE_TILE_BYTES);
+          const int krow = (int)(k_begin + (int64_t)ks * KS);
+          for (int s = 0; s < S; s++) {
+            tma_load_3d(sb + s * PLANE_TILE_BYTES, &tmap, &full_bar[st], bi * TILE, krow, s);
+            if (!diag) tma_load_3d(sb + (SMAX + s) * PLANE_TILE_BYTES, &tmap, &full_bar[st], bj * TILE, krow, s);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_i8(TILE, TILE);
+      uint32_t it = 0, n_done = 0;
+      bool alive = true;
+      for (int item = blockIdx.x; alive && item < n_items; item += gridDim.x, n_done++) {
+        const int t = item % a.tiles, sp = item / a.tiles;
+        int bi, bj;
+        tile_coords_tc(t, a.nb, bi, bj);
+        const int64_t k_begin = (int64_t)sp * per;
+        int64_t k_end = k_begin + per;
+        if (k_end > a.rows) k_end = a.rows;
+        const int nsteps = k_end > k_begin ? (int)((k_end - k_begin + KS - 1) / KS) : 0;
+        const bool diag = (bi == bj);
+        // accumulators must have been drained by the epilogue of the previous item
+        if (!mbar_wait(tmem_empty, (n_done & 1) ^ 1, a.err)) break;
+        tc_fence_after();
+        for (int ks = 0; ks < nsteps; ks++, it++) {
+          const int st = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          if (!mbar_wait(&full_bar[st], ph, a.err)) { alive = false; break; }
+          tc_fence_after();
+          const uint32_t sb = smem_u32(stage_base + st * STAGE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < KS / UMMA_K; kk++) {
+            for (int s = 0; s < S; s++) {
+              const uint64_t da = make_desc_mn_sw128(sb + s * PLANE_TILE_BYTES + kk * UMMA_K * TILE);
+              for (int tt = 0; tt + s < S; tt++) {
+                const uint32_t boff = (diag ? 0 : SMAX * PLANE_TILE_BYTES) + tt * PLANE_TILE_BYTES + kk * UMMA_K * TILE;
+                const uint64_t db = make_desc_mn_sw128(sb + boff);
+                const int d = s + tt;
+                // first contribution to accumulator d in this item: (s = 0, tt = d) at ks = 0, kk = 0
+                const uint32_t acc = (ks > 0 || kk > 0 || s > 0) ? 1u : 0u;
+                tc_mma_i8(tmem_base + d * TILE, da, db, idesc, acc);
+              }
+            }
+          }
+          tc_commit(&empty_bar[st]);  // frees the smem stage once these MMAs have read it
+        }
+        if (alive) tc_commit(tmem_full);  // accumulators complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;         // tile row held by this thread
+    uint32_t n_done = 0;
+    const double inv256 = 1.0 / 256.0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
+      const int t = item % a.tiles, sp = item / a.tiles;
+      int bi, bj;
+      tile_coords_tc(t, a.nb, bi, bj);
+      const int64_t k_begin = (int64_t)sp * per;
+      const bool empty_item = k_begin >= a.rows;
+      if (!mbar_wait(tmem_full, n_done & 1, a.err)) break;
+      tc_fence_after();
+      double *out = a.part + ((size_t)sp * a.tiles + t) * (TILE * TILE) + (size_t)row * TILE;
+      const double isc_row = __ldg(a.isc + bi * TILE + row);
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < TILE; c0 += 16) {
+        double val[16];
+        if (empty_item) {
+#pragma unroll
+          for (int q = 0; q < 16; q++) val[q] = 0.0;
+        } else {
+          int32_t v[16];
+          // Horner over the digit-pair order d = S-1 .. 0
+          tc_ld16(lane_addr + (S - 1) * TILE + c0, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 16; q++) val[q] = (double)v[q];
+          for (int d = S - 2; d >= 0; d--) {
+            tc_ld16(lane_addr + d * TILE + c0, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 16; q++) val[q] = val[q] * inv256 + (double)v[q];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) {
+          const double2 sc = *reinterpret_cast<const double2 *>(a.isc + bj * TILE + c0 + q);
+          double2 w = make_double2(val[q] * isc_row * sc.x, val[q + 1] * isc_row * sc.y);
+          double2 *p = reinterpret_cast<double2 *>(out + c0 + q);
+          if (a.accumulate) {
+            const double2 old = *p;
+            w.x += old.x;
+            w.y += old.y;
+          }
+          *p = w;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// sc_j = 2^p with colmax_j * sc_j in [2^(8S-3), 2^(8S-2));  isc_j = 256^(S-1) / sc_j
+__global__ void tc_scale_kernel(const unsigned long long *colmax_bits, double *sc, double *isc, int ldq, int S) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ldq) return;
+  const double m = __longlong_as_double((long long)colmax_bits[j]);
+  if (!(m > 0.0) || !(m < 1e300)) {
+    sc[j] = 0.0;
+    isc[j] = 0.0;
+    return;
+  }
+  int e;
+  frexp(m, &e);  // m = f * 2^e, f in [0.5, 1)  ->  m < 2^e
+  const int p = 8 * S - 2 - e;
+  sc[j] = ldexp(1.0, p);
+  isc[j] = ldexp(1.0, 8 * (S - 1) - p);
+}
+
+// fp64 G' -> S balanced base-256 digit planes (int8), 4 columns per thread
+__global__ void tc_slice_kernel(const double *G, int ldg, const double *sc, int8_t *Gq, int ldq, int64_t rows,
+                                int64_t rows_padded, int64_t plane_stride, int S) {
+  const int j = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  const int64_t c = blockIdx.x;
+  if (j >= ldq) return;
+  long long X[4] = {0, 0, 0, 0};
+  if (c < rows && j < ldg) {
+    const double2 g0 = *reinterpret_cast<const double2 *>(G + (size_t)c * ldg + j);
+    const double2 g1 = *reinterpret_cast<const double2 *>(G + (size_t)c * ldg + j + 2);
+    const double2 s0 = *reinterpret_cast<const double2 *>(sc + j);
+    const double2 s1 = *reinterpret_cast<const double2 *>(sc + j + 2);
+    X[0] = __double2ll_rn(g0.x * s0.x);
+    X[1] = __double2ll_rn(g0.y * s0.y);
+    X[2] = __double2ll_rn(g1.x * s1.x);
+    X[3] = __double2ll_rn(g1.y * s1.y);
+  }
+  for (int s = S - 1; s >= 0; s--) {  // least significant digit first
+    char4 out;
+    int8_t dd[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const long long dgt = ((X[q] + 128) & 255) - 128;
+      X[q] = (X[q] - dgt) >> 8;
+      dd[q] = (int8_t)dgt;
+    }
+    out.x = dd[0]; out.y = dd[1]; out.z = dd[2]; out.w = dd[3];
+    *reinterpret_cast<char4 *>(Gq + (size_t)s * plane_stride + (size_t)c * ldq + j) = out;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcState {
+  CUtensorMap map;
+  double *sc = nullptr, *isc = nullptr;
+  unsigned long long *colmax = nullptr;
+  int *err = nullptr;
+  int64_t rows_alloc = 0;
+  int S = 4;
+};
+
+}  // namespace
+
 int tensor_syrk_init(balm_ctx *c) {
-  balm_set_error("BALM_PREC_TENSOR: tcgen05 SYRK not built in this version");
-  return BALM_ERR_UNSUPPORTED;
+  tensor_syrk_free(c);
+  TcState *st = new TcState();
+  c->tmap = st;
+  st->S = c->slices < 2 ? 2 : (c->slices > SMAX ? SMAX : c->slices);
+  if (const char *e = getenv("BALM_TC_SLICES")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= SMAX) st->S = v;
+  }
+  const int ldq = c->ldg;
+  st->rows_alloc = (3 * c->VB + KS - 1) / KS * KS;
+  CUDA_TRY(cudaMalloc((void **)&c->Gq, (size_t)st->S * st->rows_alloc * ldq));
+  CUDA_TRY(cudaMalloc((void **)&st->sc, sizeof(double) * ldq));
+  CUDA_TRY(cudaMalloc((void **)&st->isc, sizeof(double) * ldq));
+  CUDA_TRY(cudaMalloc((void **)&st->colmax, sizeof(unsigned long long) * ldq));
+  CUDA_TRY(cudaMalloc((void **)&st->err, sizeof(int)));
+  CUDA_TRY(cudaMemset(st->err, 0, sizeof(int)));
+  c->colmax = st->colmax;  // the observation pass writes the column maxima here
+
+  EncodeTiledFn encode = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres));
+  if (!encode || qres != cudaDriverEntryPointSuccess) {
+    balm_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return BALM_ERR_CUDA;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)ldq, (cuuint64_t)st->rows_alloc, (cuuint64_t)st->S};
+  const cuuint64_t strides[2] = {(cuuint64_t)ldq, (cuuint64_t)ldq * st->rows_alloc};
+  const cuuint32_t box[3] = {TILE, KS, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode(&st->map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->Gq, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    balm_set_error("cuTensorMapEncodeTiled failed");
+    return BALM_ERR_CUDA;
+  }
+  // int32 exactness bound: every (tile, split) item contracts at most MAX_ROWS_PER_ITEM rows
+  const int64_t rows = 3 * c->VB;
+  const int min_splits = (int)((rows + MAX_ROWS_PER_ITEM - 1) / MAX_ROWS_PER_ITEM);
+  if (c->syrk_splits < min_splits) {
+    cudaFree(c->syrk_part);
+    c->syrk_splits = min_splits;
+    CUDA_TRY(cudaMalloc((void **)&c->syrk_part,
+                        sizeof(double) * (size_t)c->syrk_splits * c->syrk_tiles * TILE * TILE));
+  }
+  const int smem = STAGES * STAGE_BYTES + 1024 + 256;
+  CUDA_TRY(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  return BALM_OK;
 }
+
+void tensor_syrk_free(balm_ctx *c) {
+  if (c->tmap) {
+    TcState *st = static_cast<TcState *>(c->tmap);
+    cudaFree(st->sc); cudaFree(st->isc); cudaFree(st->colmax); cudaFree(st->err);
+    delete st;
+    c->tmap = nullptr;
+  }
+  cudaFree(c->Gq);
+  c->Gq = nullptr;
+  c->colmax = nullptr;
+}
+
+int tensor_syrk_prepare(balm_ctx *c) {  // before the observation pass of a batch: reset the column maxima
+  TcState *st = static_cast<TcState *>(c->tmap);
+  CUDA_TRY(cudaMemsetAsync(st->colmax, 0, sizeof(unsigned long long) * c->ldg, c->stream));
+  return BALM_OK;
+}
+
 int launch_tensor_syrk(balm_ctx *c, int64_t rows, bool first_batch) {
-  balm_set_error("BALM_PREC_TENSOR: tcgen05 SYRK not built in this version");
-  return BALM_ERR_UNSUPPORTED;
+  TcState *st = static_cast<TcState *>(c->tmap);
+  if (!st) { balm_set_error("tensor path not initialised"); return BALM_ERR_INVALID; }
+  const int ldq = c->ldg;
+  const int64_t rows_padded = (rows + KS - 1) / KS * KS;
+  tc_scale_kernel<<<(ldq + 255) / 256, 256, 0, c->stream>>>(st->colmax, st->sc, st->isc, ldq, st->S);
+  dim3 sgrid((unsigned)rows_padded, (ldq / 4 + 127) / 128);
+  tc_slice_kernel<<<sgrid, 128, 0, c->stream>>>(c->G, c->ldg, st->sc, c->Gq, ldq, rows, rows_padded,
+                                                (int64_t)st->rows_alloc * ldq, st->S);
+  CUDA_TRY(cudaEventRecord(c->ev[12], c->stream));  // end of the slice phase
+  TcArgs a{rows_padded, c->syrk_nb, c->syrk_tiles, c->syrk_splits, st->S, st->isc, c->syrk_part,
+           first_batch ? 0 : 1, st->err};
+  const int items = a.tiles * a.splits;
+  const int grid = items < c->sm_count ? items : c->sm_count;
+  const int smem = STAGES * STAGE_BYTES + 1024 + 256;
+  syrk_tc_kernel<<<grid, TC_THREADS, smem, c->stream>>>(st->map, a);
+  c->launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return BALM_OK;
 }
-void tensor_syrk_free(balm_ctx *c) {}
+
+int tensor_syrk_check(balm_ctx *c) {
+  TcState *st = static_cast<TcState *>(c->tmap);
+  if (!st) return BALM_OK;
+  int e = 0;
+  CUDA_TRY(cudaMemcpyAsync(&e, st->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (e != 0) {
+    balm_set_error("tcgen05 SYRK pipeline timed out (mbarrier wait bound exceeded)");
+    return BALM_ERR_CUDA;
+  }
+  return BALM_OK;
+}

@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--impl", default="balm_b200")
     ap.add_argument("--poses", type=int, default=500)
     ap.add_argument("--voxels", type=int, default=100000, help="plane voxels per GPU")
-    ap.add_argument("--precision", default=os.environ.get("BALM_BENCH_PRECISION", "fp64"), choices=["fp64", "tensor"])
+    ap.add_argument("--precision", default=os.environ.get("BALM_BENCH_PRECISION", "tensor"), choices=["fp64", "tensor"])
     ap.add_argument("--cpu-sample-voxels", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -38,6 +38,13 @@ def _pose_err(a, b):
     return rot, tra
 
 
+PRECS = [pytest.param(0, id="fp64"), pytest.param(1, id="tensor")]
+# Hessian tolerance: fp64 path 1e-9; tcgen05 split-integer path: G' is rounded to 30 bits below
+# each column maximum before the EXACT integer accumulation -> 1e-8 of max|H| (measured 2e-10 .. 4e-9)
+TOLH = {0: 1e-9, 1: 1e-8}
+
+
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("n_poses,n_planes,drop,with_fix", [
     (6, 40, 0.0, False),      # dense, one warp tile
     (50, 300, 0.0, False),    # dense, benchmark_virtual C1 shape (scaled down in M)
@@ -47,18 +54,18 @@ def _pose_err(a, b):
     (9, 30, 0.5, True),       # sparse + fix
     (2, 5, 0.0, False),       # minimum: two poses
 ])
-def test_evaluate_matches_oracle(n_poses, n_planes, drop, with_fix):
+def test_evaluate_matches_oracle(n_poses, n_planes, drop, with_fix, prec):
     sc = scenes.make_scene(n_poses=n_poses, n_planes=n_planes, seed=21, drop=drop, with_fix=with_fix)
-    c, o = _ctx(sc), _oracle(sc)
-    _check_eval(c, o, sc["poses_init"])
+    c, o = _ctx(sc, prec), _oracle(sc)
+    _check_eval(c, o, sc["poses_init"], tolH=TOLH[prec])
     if with_fix:
-        _check_eval(c, o, sc["poses_init"], include_fix=True)
+        _check_eval(c, o, sc["poses_init"], include_fix=True, tolH=TOLH[prec])
     r = c.residual(sc["poses_init"])
     ro = o.residual(sc["poses_init"])
     assert abs(r - ro) <= 1e-12 * abs(ro)
     # at the ground truth as well: lambda_min sits at the noise floor (1e-4) of a covariance whose raw second
     # moments are O(10), so ANY fp64 evaluation (the oracle included) carries eps*|P/N|/lambda_min ~ 1e-11
-    _check_eval(c, o, sc["poses_gt"], tolr=1e-10)
+    _check_eval(c, o, sc["poses_gt"], tolr=1e-10, tolH=TOLH[prec])
 
 
 def test_voxel_range_semantics():
@@ -73,21 +80,23 @@ def test_voxel_range_semantics():
     assert r0 == 0 and not H0.any() and not g0.any()
 
 
-def test_batched_evaluation_equals_single_batch(monkeypatch):
+@pytest.mark.parametrize("prec", PRECS)
+def test_batched_evaluation_equals_single_batch(monkeypatch, prec):
     sc = scenes.make_scene(n_poses=16, n_planes=300, seed=23)
-    c1 = _ctx(sc)
+    c1 = _ctx(sc, prec)
     H1, g1, r1 = c1.evaluate(sc["poses_init"])
     monkeypatch.setenv("BALM_G_BUDGET_MB", "1")  # 1 MiB of G' -> many voxel batches
-    c2 = _ctx(sc)
+    c2 = _ctx(sc, prec)
     H2, g2, r2 = c2.evaluate(sc["poses_init"])
-    assert np.abs(H1 - H2).max() <= 1e-12 * np.abs(H1).max()
+    assert np.abs(H1 - H2).max() <= (1e-12 if prec == 0 else 2e-8) * np.abs(H1).max()
     assert np.abs(g1 - g2).max() <= 1e-12 * np.abs(g1).max()
     assert abs(r1 - r2) <= 1e-13 * abs(r1)
 
 
-def test_run_to_run_deterministic():
+@pytest.mark.parametrize("prec", PRECS)
+def test_run_to_run_deterministic(prec):
     sc = scenes.make_scene(n_poses=24, n_planes=200, seed=24)
-    c = _ctx(sc)
+    c = _ctx(sc, prec)
     H1, g1, r1 = c.evaluate(sc["poses_init"])
     H2, g2, r2 = c.evaluate(sc["poses_init"])
     assert np.array_equal(H1, H2) and np.array_equal(g1, g2) and r1 == r2
@@ -105,10 +114,11 @@ def test_solve_matches_oracle_ldlt():
         assert abs(q1 - q1o) <= 1e-9 * abs(q1o)
 
 
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("n_poses,n_planes,drop", [(8, 60, 0.0), (50, 400, 0.0), (20, 300, 0.3)])
-def test_damping_iter_matches_oracle_per_iteration(n_poses, n_planes, drop):
+def test_damping_iter_matches_oracle_per_iteration(n_poses, n_planes, drop, prec):
     sc = scenes.make_scene(n_poses=n_poses, n_planes=n_planes, seed=26, drop=drop)
-    c, o = _ctx(sc), _oracle(sc)
+    c, o = _ctx(sc, prec), _oracle(sc)
     poses, tr, per = c.damping_iter(sc["poses_init"], want_per_iter=True, gauge_mode=2)
     st, poses_o, tr_o, per_o = o.damping_iter(sc["poses_init"], gauge_mode=2)
     assert st == 0 and len(tr) == len(tr_o)
@@ -117,7 +127,7 @@ def test_damping_iter_matches_oracle_per_iteration(n_poses, n_planes, drop):
         rot, tra = _pose_err(per[it], per_o[it])
         assert rot <= 1e-6 and tra <= 1e-6, (it, rot, tra)   # north_star: 1e-6 rad / 1e-6 m per iteration
         assert abs(tr[it]["r2"] - tr_o[it]["r2"]) <= 1e-9 * abs(tr_o[it]["r2"])
-        assert abs(tr[it]["u"] - tr_o[it]["u"]) <= 1e-6 * tr_o[it]["u"]
+        assert abs(tr[it]["u"] - tr_o[it]["u"]) <= 1e-5 * tr_o[it]["u"]
     # final gauge step (bavoxel.hpp:1159-1164) and the benchmark_virtual variant
     p0, _, _ = c.damping_iter(sc["poses_init"], gauge_mode=0)
     _, p0o, _, _ = o.damping_iter(sc["poses_init"], gauge_mode=0)
@@ -165,10 +175,11 @@ def test_reference_call_surface_mirror():
     assert max(_pose_err(bavoxel.pack_poses(xs), po)) <= 1e-6
 
 
-def test_synth_scene_roundtrip_and_parity_c1():
+@pytest.mark.parametrize("prec", PRECS)
+def test_synth_scene_roundtrip_and_parity_c1(prec):
     """BASELINE config C1 (50 poses, 2k plane voxels) generated in HBM, downloaded, checked against the oracle."""
     import balm_b200
-    c = balm_b200.Context(50, 0, 0)
+    c = balm_b200.Context(50, 0, prec)
     gt, init = c.synth_virtual(2000, seed=10)
     row_ptr, pose_idx, obs10, coe = c.download_voxels()
     assert row_ptr[-1] == 100000 and np.all(coe == 50 * 40) and np.all(obs10[:, 9] == 40)
@@ -177,22 +188,23 @@ def test_synth_scene_roundtrip_and_parity_c1():
     Ho, go, ro = o.evaluate_threads(init, threads=4)
     assert abs(r - ro) <= 1e-12 * abs(ro)
     assert np.abs(g - go).max() <= 1e-10 * np.abs(go).max()
-    assert np.abs(H - Ho).max() <= 1e-9 * np.abs(Ho).max()
+    assert np.abs(H - Ho).max() <= TOLH[prec] * np.abs(Ho).max()
     # the planes are planes: at ground truth the cost sits at the point-noise floor  sum coe * sigma^2
     assert 0.8 < c.residual(gt) / (coe.sum() * 1e-4) < 1.2
     # host-buffer path (balm_set_voxels) reproduces the HBM-resident one bit for bit
-    c2 = balm_b200.Context(50, 0, 0)
+    c2 = balm_b200.Context(50, 0, prec)
     c2.set_voxels(row_ptr, pose_idx, obs10, coe)
     H2, g2, r2 = c2.evaluate(init)
     assert np.array_equal(H, H2) and np.array_equal(g, g2) and r == r2
 
 
-def test_full_size_properties_c3():
+@pytest.mark.parametrize("prec", PRECS)
+def test_full_size_properties_c3(prec):
     """BASELINE config C3 (500 poses, 100k voxels): too big for the oracle, so size-independent properties:
     gauge null space (Supplementary eq. 170-185), symmetry, residual consistency, LM monotone decrease."""
     import balm_b200
     N, M = 500, 100000
-    c = balm_b200.Context(N, 0, 0)
+    c = balm_b200.Context(N, 0, prec)
     gt, init = c.synth_virtual(M, seed=10)
     H, g, r = c.evaluate(init)
     assert np.array_equal(H, H.T)
@@ -200,11 +212,11 @@ def test_full_size_properties_c3():
     rng = np.random.default_rng(0)
     dT = np.tile(rng.normal(size=6), N)
     assert abs(g @ dT) <= 1e-8 * np.abs(g).max() * np.linalg.norm(dT)
-    assert abs(dT @ H @ dT) <= 1e-8 * np.abs(H).max() * (dT @ dT)
+    assert abs(dT @ H @ dT) <= (1e-8 if prec == 0 else 1e-7) * np.abs(H).max() * (dT @ dT)
     # linearity in the voxel set: two halves add up
     Ha, ga, ra = c.evaluate(init, 0, M // 2)
     Hb, gb, rb = c.evaluate(init, M // 2, M)
-    assert np.abs(Ha + Hb - H).max() <= 1e-11 * np.abs(H).max()
+    assert np.abs(Ha + Hb - H).max() <= (1e-11 if prec == 0 else 2e-9) * np.abs(H).max()
     poses, tr, _ = c.damping_iter(init, max_iter=6)
     costs = [t["r2"] for t in tr if t["accepted"]]
     assert len(costs) >= 3 and all(b <= a for a, b in zip(costs, costs[1:]))
@@ -215,3 +227,27 @@ def test_full_size_properties_c3():
 def _gauge(p):
     R0, p0 = scenes.unpack_pose(p[0])
     return scenes.pack_poses([R0.T @ scenes.unpack_pose(x)[0] for x in p], [R0.T @ (x[9:] - p0) for x in p])
+
+
+def test_tensor_path_matches_fp64_path_c2():
+    """BASELINE config C2 shape (200 poses, 20k voxels): tcgen05 split-integer SYRK vs the fp64 DMMA path on the
+    same device data, and the pose update they imply (north_star: 1e-6 rad / 1e-6 m per iteration)."""
+    import balm_b200
+    N, M = 200, 20000
+    out = {}
+    for prec in (0, 1):
+        c = balm_b200.Context(N, 0, prec)
+        gt, init = c.synth_virtual(M, seed=11)
+        H, g, r = c.evaluate(init)
+        dx, q1, bad = c.solve(0.01)
+        poses, tr, per = c.damping_iter(init, want_per_iter=True, gauge_mode=2)
+        out[prec] = (H, g, r, dx, per, tr)
+        c.close()
+    H0, g0, r0, dx0, per0, tr0 = out[0]
+    H1, g1, r1, dx1, per1, tr1 = out[1]
+    assert np.array_equal(g0, g1) and r0 == r1           # the O(K) passes are shared
+    assert np.abs(H1 - H0).max() <= 1e-8 * np.abs(H0).max()
+    assert np.abs(dx1 - dx0).max() <= 1e-7
+    assert [t["accepted"] for t in tr0] == [t["accepted"] for t in tr1]
+    for a, b in zip(per0, per1):
+        assert max(_pose_err(a, b)) <= 1e-6
