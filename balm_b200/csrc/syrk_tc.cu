@@ -79,14 +79,26 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
                : "memory");
 }
 
+// USAGE: collector behaviour of the A operand (consecutive MMAs sharing A keep it in the collector buffer
+// instead of re-reading 4 KB of shared memory; SASS A_KEEP / A_REUSE). 0 none, 1 fill, 2 use, 3 lastuse.
+#define BALM_MMA_I8(QUAL)                                                                    \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                            \
+               "tcgen05.mma.cta_group::1.kind::i8" QUAL " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), \
+               "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)                         \
+               : "memory")
+template <int USAGE>
 __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (USAGE == 1) BALM_MMA_I8(".collector::a::fill");
+  else if constexpr (USAGE == 2) BALM_MMA_I8(".collector::a::use");
+  else if constexpr (USAGE == 3) BALM_MMA_I8(".collector::a::lastuse");
+  else BALM_MMA_I8("");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
 }
 
 // 32 lanes x 16 consecutive 32-bit columns
@@ -127,6 +139,7 @@ struct TcArgs {
   double *part;       // [splits][tiles][128*128]
   int accumulate;
   int *err;
+  int collector;
 };
 
 __device__ __forceinline__ void tile_coords_tc(int t, int nb, int &bi, int &bj) {
@@ -134,6 +147,69 @@ __device__ __forceinline__ void tile_coords_tc(int t, int nb, int &bi, int &bj) 
   while (rem >= nb - r) { rem -= nb - r; r++; }
   bi = r;
   bj = r + rem;
+}
+
+// The MMA issue loop runs in ONE thread, so its scalar overhead per UTCIMMA bounds the tensor pipe: everything
+// that can be a compile-time constant is (digit-plane count, the (s,t) pair list, descriptor offsets), and a
+// descriptor is the stage's base word plus a constant (the 14-bit start-address field never carries).
+template <int S, bool COLLECT>
+__device__ __forceinline__ void mma_issue_loop(const TcArgs &a, uint8_t *stage_base, uint64_t *full_bar,
+                                               uint64_t *empty_bar, uint64_t *tmem_full, uint64_t *tmem_empty,
+                                               uint32_t tmem_base, int n_items, int64_t per) {
+  constexpr uint32_t idesc = make_idesc_i8(TILE, TILE);
+  constexpr uint32_t PLANE_U = PLANE_TILE_BYTES >> 4;     // descriptor units (16 B) between digit planes
+  constexpr uint32_t KK_U = (UMMA_K * TILE) >> 4;         // ... between K=32 sub-steps
+  const uint64_t desc_hi = make_desc_mn_sw128(0) & 0xFFFFFFFF00000000ull;
+  const uint32_t desc_lo_fixed = (uint32_t)(make_desc_mn_sw128(0) & 0xFFFFFFFFull);  // LBO field
+  uint32_t it = 0, n_done = 0;
+  bool alive = true;
+  for (int item = blockIdx.x; alive && item < n_items; item += gridDim.x, n_done++) {
+    const int t = item % a.tiles, sp = item / a.tiles;
+    int bi, bj;
+    tile_coords_tc(t, a.nb, bi, bj);
+    const int64_t k_begin = (int64_t)sp * per;
+    int64_t k_end = k_begin + per;
+    if (k_end > a.rows) k_end = a.rows;
+    const int nsteps = k_end > k_begin ? (int)((k_end - k_begin + KS - 1) / KS) : 0;
+    const uint32_t b_off = (bi == bj) ? 0u : SMAX * PLANE_U;
+    // accumulators must have been drained by the epilogue of the previous item
+    if (!__all_sync(0xffffffffu, mbar_wait(tmem_empty, (n_done & 1) ^ 1, a.err))) break;
+    tc_fence_after();
+    for (int ks = 0; ks < nsteps; ks++, it++) {
+      const int st = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      if (!__all_sync(0xffffffffu, mbar_wait(&full_bar[st], ph, a.err))) { alive = false; break; }
+      tc_fence_after();
+      const uint32_t lo_a = desc_lo_fixed + ((smem_u32(stage_base + st * STAGE_BYTES) & 0x3FFFF) >> 4);
+      const uint32_t lo_b = lo_a + b_off;
+      const uint32_t acc0 = ks > 0 ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < KS / UMMA_K; kk++) {
+#pragma unroll
+          for (int s = 0; s < S; s++) {
+            const uint64_t da = desc_hi | (uint64_t)(lo_a + s * PLANE_U + kk * KK_U);
+#pragma unroll
+            for (int tt = 0; tt + s < S; tt++) {
+              const uint64_t db = desc_hi | (uint64_t)(lo_b + tt * PLANE_U + kk * KK_U);
+              // first contribution to accumulator d = s + tt of this item: s == 0 at ks == 0, kk == 0
+              const uint32_t acc = (s > 0 || kk > 0) ? 1u : acc0;
+              constexpr int group = S;  // placeholder to keep the expression below readable
+              (void)group;
+              if (!COLLECT || S - s == 1) tc_mma_i8<0>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+              else if (tt == 0) tc_mma_i8<1>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+              else if (tt == S - s - 1) tc_mma_i8<3>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+              else tc_mma_i8<2>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+            }
+          }
+        }
+        tc_commit(&empty_bar[st]);  // frees the smem stage once these MMAs have read it
+      }
+      __syncwarp();
+    }
+    if (alive && elect_one()) tc_commit(tmem_full);  // accumulators complete
+    __syncwarp();
+  }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
@@ -198,46 +274,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_i8(TILE, TILE);
-      uint32_t it = 0, n_done = 0;
-      bool alive = true;
-      for (int item = blockIdx.x; alive && item < n_items; item += gridDim.x, n_done++) {
-        const int t = item % a.tiles, sp = item / a.tiles;
-        int bi, bj;
-        tile_coords_tc(t, a.nb, bi, bj);
-        const int64_t k_begin = (int64_t)sp * per;
-        int64_t k_end = k_begin + per;
-        if (k_end > a.rows) k_end = a.rows;
-        const int nsteps = k_end > k_begin ? (int)((k_end - k_begin + KS - 1) / KS) : 0;
-        const bool diag = (bi == bj);
-        // accumulators must have been drained by the epilogue of the previous item
-        if (!mbar_wait(tmem_empty, (n_done & 1) ^ 1, a.err)) break;
-        tc_fence_after();
-        for (int ks = 0; ks < nsteps; ks++, it++) {
-          const int st = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          if (!mbar_wait(&full_bar[st], ph, a.err)) { alive = false; break; }
-          tc_fence_after();
-          const uint32_t sb = smem_u32(stage_base + st * STAGE_BYTES);
-#pragma unroll
-          for (int kk = 0; kk < KS / UMMA_K; kk++) {
-            for (int s = 0; s < S; s++) {
-              const uint64_t da = make_desc_mn_sw128(sb + s * PLANE_TILE_BYTES + kk * UMMA_K * TILE);
-              for (int tt = 0; tt + s < S; tt++) {
-                const uint32_t boff = (diag ? 0 : SMAX * PLANE_TILE_BYTES) + tt * PLANE_TILE_BYTES + kk * UMMA_K * TILE;
-                const uint64_t db = make_desc_mn_sw128(sb + boff);
-                const int d = s + tt;
-                // first contribution to accumulator d in this item: (s = 0, tt = d) at ks = 0, kk = 0
-                const uint32_t acc = (ks > 0 || kk > 0 || s > 0) ? 1u : 0u;
-                tc_mma_i8(tmem_base + d * TILE, da, db, idesc, acc);
-              }
-            }
-          }
-          tc_commit(&empty_bar[st]);  // frees the smem stage once these MMAs have read it
-        }
-        if (alive) tc_commit(tmem_full);  // accumulators complete
-      }
+    if (a.collector) {
+      if (S == 4) mma_issue_loop<4, true>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
+      else if (S == 3) mma_issue_loop<3, true>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
+      else mma_issue_loop<2, true>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
+    } else {
+      if (S == 4) mma_issue_loop<4, false>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
+      else if (S == 3) mma_issue_loop<3, false>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
+      else mma_issue_loop<2, false>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -446,7 +490,7 @@ int launch_tensor_syrk(balm_ctx *c, int64_t rows, bool first_batch) {
                                                 (int64_t)st->rows_alloc * ldq, st->S);
   CUDA_TRY(cudaEventRecord(c->ev[12], c->stream));  // end of the slice phase
   TcArgs a{rows_padded, c->syrk_nb, c->syrk_tiles, c->syrk_splits, st->S, st->isc, c->syrk_part,
-           first_batch ? 0 : 1, st->err};
+           first_batch ? 0 : 1, st->err, getenv("BALM_TC_COLLECTOR") ? 1 : 0};
   const int items = a.tiles * a.splits;
   const int grid = items < c->sm_count ? items : c->sm_count;
   const int smem = STAGES * STAGE_BYTES + 1024 + 256;

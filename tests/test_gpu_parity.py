@@ -126,7 +126,7 @@ def test_damping_iter_matches_oracle_per_iteration(n_poses, n_planes, drop, prec
     for it in range(len(tr)):
         rot, tra = _pose_err(per[it], per_o[it])
         assert rot <= 1e-6 and tra <= 1e-6, (it, rot, tra)   # north_star: 1e-6 rad / 1e-6 m per iteration
-        assert abs(tr[it]["r2"] - tr_o[it]["r2"]) <= 1e-9 * abs(tr_o[it]["r2"])
+        assert abs(tr[it]["r2"] - tr_o[it]["r2"]) <= (1e-9 if prec == 0 else 1e-7) * abs(tr_o[it]["r2"])
         assert abs(tr[it]["u"] - tr_o[it]["u"]) <= 1e-5 * tr_o[it]["u"]
     # final gauge step (bavoxel.hpp:1159-1164) and the benchmark_virtual variant
     p0, _, _ = c.damping_iter(sc["poses_init"], gauge_mode=0)
