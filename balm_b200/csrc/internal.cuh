@@ -51,6 +51,11 @@ struct balm_ctx {
   double *W = nullptr;                              // [n*NB] panel * D
   double *dx = nullptr;                             // [n]
   double *dvec = nullptr;                           // [n] diag(H)
+  double *Xinv = nullptr;                           // [panels][64*64] inverses of the unit-lower diagonal blocks
+  double *dinv = nullptr;                           // [n] 1/d
+  double *sol = nullptr;                            // [n] right-hand side / forward-substitution vector
+  void *solve_graph = nullptr;                      // cudaGraphExec_t of the solve sequence
+  int solve_launches = 0;
   double *scal = nullptr;                           // device scalars [16]
   double *h_scal = nullptr;                         // pinned host mirror [16]
   int *flags = nullptr;                             // device flags [4] (0: ldlt bad pivot)

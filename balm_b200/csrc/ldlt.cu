@@ -11,16 +11,19 @@
 // not depend on the pivot order beyond rounding.
 //
 // A is column-major n x n; only the lower triangle is read/written. Panel width NB = 64.
+#include <stdlib.h>
 #include "internal.cuh"
+#define TRY_LAUNCH(x) do { int _s = (x); if (_s != BALM_OK) return _s; } while (0)
 
 namespace {
 
 constexpr int NB = BALM_NB;
 
-__global__ void damp_copy_kernel(const double *H, double *A, double *dvec, int n, double u) {
+__global__ void damp_copy_kernel(const double *H, double *A, double *dvec, int n, const double *u_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // row (contiguous)
   const int j = blockIdx.y;
   if (i >= n) return;
+  const double u = *u_dev;
   double h = H[(size_t)j * n + i];
   if (i == j) {
     dvec[i] = h;
@@ -29,171 +32,242 @@ __global__ void damp_copy_kernel(const double *H, double *A, double *dvec, int n
   A[(size_t)j * n + i] = h;
 }
 
-// Factor the nbw x nbw diagonal block at j0 in shared memory: unit-lower L11 (strict lower part) and d.
-__global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0, int nbw, int *flags) {
-  __shared__ double S[NB][NB + 1];
-  __shared__ double colj[NB];
-  const int tid = threadIdx.x;
-  for (int e = tid; e < nbw * nbw; e += 256) {
-    const int r = e % nbw, c = e / nbw;
-    S[r][c] = (r >= c) ? A[(size_t)(j0 + c) * n + j0 + r] : 0.0;
+// ---- panel step j0: three kernels ------------------------------------------------------------------------
+// (1) ldl_diag_kernel: one CTA factors the 64x64 diagonal block in REGISTERS (16x16 threads, 4x4 each), one
+//     __syncthreads per column (double-buffered column broadcast). The same sweep builds X = L11^-1 (forward
+//     substitution on the identity), so the panel below needs a GEMM instead of a sequential TRSM, and applies
+//     it to the right-hand side: y_j = L11^-1 b_j (forward substitution fused into the factorisation).
+// (2) ldl_panel_kernel: W = A21 X^T (64x64x64 GEMM per 64-row tile), L21 = W d^-1, b_rows -= L21 y_j.
+// (3) ldl_update_kernel: A22 -= L21 W^T on 128x128 tiles of the lower triangle.
+__global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0, int nbw, double *Xcm, double *dinv_all,
+                                                       double *sol, int *flags) {
+  __shared__ double colA[2][NB], rowX[2][NB], bvec[NB], ypart[NB];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // rows 4*tx.., cols 4*ty..
+  double a[4][4], x[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; p++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int r = 4 * tx + p, c = 4 * ty + q;
+      double v = (r == c) ? 1.0 : 0.0;  // padding rows/cols of a short last panel act as identity
+      if (r < nbw && c < nbw && r >= c) v = A[(size_t)(j0 + c) * n + j0 + r];
+      a[p][q] = v;
+      x[p][q] = (r == c) ? 1.0 : 0.0;
+    }
+  if (tid < NB) bvec[tid] = tid < nbw ? sol[j0 + tid] : 0.0;
+  bool bad = false;
+#pragma unroll 1
+  for (int jq = 0; jq < NB / 4; jq++) {
+#pragma unroll
+    for (int jr = 0; jr < 4; jr++) {  // compile-time register indices
+      const int j = 4 * jq + jr, buf = jr & 1;
+      if (ty == jq) {
+#pragma unroll
+        for (int p = 0; p < 4; p++) colA[buf][4 * tx + p] = a[p][jr];
+      }
+      if (tx == jq) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) rowX[buf][4 * ty + q] = x[jr][q];
+      }
+      __syncthreads();
+      const double d = colA[buf][j];
+      if (!(fabs(d) > 1e-290 && fabs(d) < 1e300)) bad = true;
+      const double dinv = 1.0 / d;
+      double lr[4], cc[4], xr[4];
+#pragma unroll
+      for (int p = 0; p < 4; p++) lr[p] = colA[buf][4 * tx + p] * dinv;  // L[r][j]
+#pragma unroll
+      for (int q = 0; q < 4; q++) { cc[q] = colA[buf][4 * ty + q]; xr[q] = rowX[buf][4 * ty + q]; }
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        const int r = 4 * tx + p;
+        if (r > j) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int c = 4 * ty + q;
+            if (c > j && r >= c) a[p][q] -= lr[p] * cc[q];
+            x[p][q] -= lr[p] * xr[q];
+          }
+          if (ty == jq) a[p][jr] = lr[p];
+        }
+      }
+    }
+  }
+  if (bad && tid == 0) atomicOr(&flags[0], 1);
+  // write back L11 (strict lower) and d (diagonal); X column-major; d^-1
+#pragma unroll
+  for (int p = 0; p < 4; p++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int r = 4 * tx + p, c = 4 * ty + q;
+      if (r < nbw && c < nbw && r >= c) A[(size_t)(j0 + c) * n + j0 + r] = a[p][q];
+      Xcm[c * NB + r] = x[p][q];
+      if (r == c && r < nbw) dinv_all[j0 + r] = 1.0 / a[p][q];
+    }
+  // y_j = X b_j : partial over this thread's 4 columns, reduced over ty through shared memory
+  __syncthreads();
+  if (tid < NB) ypart[tid] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) s += x[p][q] * bvec[4 * ty + q];
+    atomicAdd(&ypart[4 * tx + p], s);
   }
   __syncthreads();
-  for (int j = 0; j < nbw; j++) {
-    const double d = S[j][j];
-    if (tid == 0 && !(fabs(d) > 1e-290 && fabs(d) < 1e300)) atomicOr(&flags[0], 1);
-    for (int i = j + 1 + tid; i < nbw; i += 256) colj[i] = S[i][j];
-    __syncthreads();
-    const double dinv = 1.0 / d;
-    const int m = nbw - j - 1;
-    for (int e = tid; e < m * m; e += 256) {
-      const int r = j + 1 + e % m, c = j + 1 + e / m;
-      if (r >= c) S[r][c] -= colj[r] * colj[c] * dinv;
-    }
-    for (int i = j + 1 + tid; i < nbw; i += 256) S[i][j] = colj[i] * dinv;
-    __syncthreads();
-  }
-  for (int e = tid; e < nbw * nbw; e += 256) {
-    const int r = e % nbw, c = e / nbw;
-    if (r >= c) A[(size_t)(j0 + c) * n + j0 + r] = S[r][c];
-  }
+  if (tid < nbw) sol[j0 + tid] = ypart[tid];
 }
 
-// Rows below the diagonal block: W = A21 * L11^-T (unit), L21 = W * d^-1. One thread per row.
-__global__ void __launch_bounds__(NB) ldl_panel_kernel(double *A, double *W, int n, int j0, int nbw) {
+__global__ void __launch_bounds__(256) ldl_panel_kernel(double *A, double *W, int n, int j0, int nbw, const double *Xcm,
+                                                        const double *dinv_all, double *sol) {
   extern __shared__ double dyn_smem[];
-  double (*L11)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
-  double (*rowbuf)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
-  double *dinv = dyn_smem + 2 * NB * (NB + 1);
-  const int tid = threadIdx.x;
+  double (*sA)[NB + 4] = reinterpret_cast<double (*)[NB + 4]>(dyn_smem);                  // [k][row]
+  double (*sX)[NB + 4] = reinterpret_cast<double (*)[NB + 4]>(dyn_smem + NB * (NB + 4));  // [k][col] = X[col][k]
+  __shared__ double yj[NB], dv[NB];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int i0 = j0 + nbw + blockIdx.x * NB;
-  for (int e = tid; e < nbw * nbw; e += NB) {
-    const int r = e % nbw, c = e / nbw;
-    L11[r][c] = A[(size_t)(j0 + c) * n + j0 + r];
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e & (NB - 1), k = e >> 6;
+    sA[k][r] = (k < nbw && i0 + r < n) ? A[(size_t)(j0 + k) * n + i0 + r] : 0.0;
+    sX[k][r] = Xcm[k * NB + r];  // X[r][k]
+  }
+  if (tid < NB) {
+    yj[tid] = tid < nbw ? sol[j0 + tid] : 0.0;
+    dv[tid] = tid < nbw ? dinv_all[j0 + tid] : 0.0;
   }
   __syncthreads();
-  if (tid < nbw) dinv[tid] = 1.0 / L11[tid][tid];
-  const int i = i0 + tid;
-  const bool ok = i < n;
-  if (ok)
-    for (int c = 0; c < nbw; c++) rowbuf[tid][c] = A[(size_t)(j0 + c) * n + i];
+  double acc[4][4] = {};
+#pragma unroll 8
+  for (int k = 0; k < NB; k++) {
+    double av[4], xv[4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) { av[p] = sA[k][4 * tx + p]; xv[p] = sX[k][4 * ty + p]; }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[p][q] += av[p] * xv[q];
+  }
   __syncthreads();
-  if (ok) {
-    for (int c = 0; c < nbw; c++) {
-      double w = rowbuf[tid][c];
-      for (int t = 0; t < c; t++) w -= rowbuf[tid][t] * L11[c][t];
-      rowbuf[tid][c] = w;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int c = 4 * ty + q;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const int r = 4 * tx + p, i = i0 + r;
+      const double l = acc[p][q] * dv[c];
+      sA[c][r] = l;  // reuse as L21 tile [c][r] for the right-hand-side update
+      if (c < nbw && i < n) {
+        W[(size_t)c * n + i] = acc[p][q];
+        A[(size_t)(j0 + c) * n + i] = l;
+      }
     }
-    for (int c = 0; c < nbw; c++) {
-      const double w = rowbuf[tid][c];
-      W[(size_t)c * n + i] = w;
-      A[(size_t)(j0 + c) * n + i] = w * dinv[c];
-    }
+  }
+  __syncthreads();
+  if (tid < NB && i0 + tid < n) {
+    double s = 0.0;
+#pragma unroll 8
+    for (int c = 0; c < NB; c++) s += sA[c][tid] * yj[c];
+    sol[i0 + tid] -= s;
   }
 }
 
-// Trailing update A22 -= L21 * W^T on 64x64 tiles of the lower triangle. 256 threads, 4x4 per thread.
+constexpr int UT = 128;  // update tile
+constexpr int UK = 32;   // k chunk
 __global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double *W, int n, int j0, int nbw) {
   extern __shared__ double dyn_smem[];
-  double (*sL)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);                  // [c][row]
-  double (*sW)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));  // [c][col]
+  double (*sL)[UT + 4] = reinterpret_cast<double (*)[UT + 4]>(dyn_smem);                  // [k][row]
+  double (*sW)[UT + 4] = reinterpret_cast<double (*)[UT + 4]>(dyn_smem + UK * (UT + 4));  // [k][col]
   const int base = j0 + nbw;
-  // tile enumeration over the lower triangle of the trailing matrix
   int t = blockIdx.x, tr = 0;
   while (t >= tr + 1) { t -= tr + 1; tr++; }
   const int tc = t;  // tc <= tr
-  const int r0 = base + tr * NB, c0 = base + tc * NB;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < nbw * NB; e += 256) {
-    const int rr = e % NB, c = e / NB;
-    sL[c][rr] = (r0 + rr < n) ? A[(size_t)(j0 + c) * n + r0 + rr] : 0.0;
-    sW[c][rr] = (c0 + rr < n) ? W[(size_t)c * n + c0 + rr] : 0.0;
+  const int r0 = base + tr * UT, c0 = base + tc * UT;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double acc[8][8] = {};
+  for (int k0 = 0; k0 < nbw; k0 += UK) {
+    __syncthreads();
+    for (int e = tid; e < UK * UT; e += 256) {
+      const int rr = e & (UT - 1), k = e >> 7;
+      const bool kv = k0 + k < nbw;
+      sL[k][rr] = (kv && r0 + rr < n) ? A[(size_t)(j0 + k0 + k) * n + r0 + rr] : 0.0;
+      sW[k][rr] = (kv && c0 + rr < n) ? W[(size_t)(k0 + k) * n + c0 + rr] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < UK; k++) {
+      double lv[8], wv[8];
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        lv[p] = sL[k][4 * tx + p];
+        lv[4 + p] = sL[k][64 + 4 * tx + p];
+        wv[p] = sW[k][4 * ty + p];
+        wv[4 + p] = sW[k][64 + 4 * ty + p];
+      }
+#pragma unroll
+      for (int p = 0; p < 8; p++)
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[p][q] += lv[p] * wv[q];
+    }
   }
-  __syncthreads();
-  const int tx = tid % 16, ty = tid / 16;  // rows tx*4.., cols ty*4..
-  double acc[4][4] = {};
-  for (int c = 0; c < nbw; c++) {
-    double lv[4], wv[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) { lv[q] = sL[c][tx * 4 + q]; wv[q] = sW[c][ty * 4 + q]; }
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int b = 0; b < 4; b++) acc[a][b] += lv[a] * wv[b];
-  }
-#pragma unroll
-  for (int b = 0; b < 4; b++) {
-    const int col = c0 + ty * 4 + b;
+  for (int q = 0; q < 8; q++) {
+    const int col = c0 + (q < 4 ? 4 * ty + q : 64 + 4 * ty + q - 4);
     if (col >= n) continue;
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-      const int row = r0 + tx * 4 + a;
-      if (row < n && row >= col) A[(size_t)col * n + row] -= acc[a][b];
+    for (int p = 0; p < 8; p++) {
+      const int row = r0 + (p < 4 ? 4 * tx + p : 64 + 4 * tx + p - 4);
+      if (row < n && row >= col) A[(size_t)col * n + row] -= acc[p][q];
     }
   }
 }
 
-// Single-CTA triangular solves: x = L^-T diag(d)^-1 L^-1 (-g); also q1. 1024 threads.
-__global__ void __launch_bounds__(1024) ldl_solve_kernel(const double *A, const double *g, const double *dvec,
-                                                        double *x, int n, double u, double *scal) {
-  extern __shared__ double sx[];  // n doubles
-  __shared__ double sblk[NB];
+// rhs = -g (start of the forward substitution, fused into the factorisation kernels)
+__global__ void rhs_init_kernel(const double *g, double *sol, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sol[i] = -g[i];
+}
+
+// Backward substitution L^T x = w (w = d^-1 y, scaled beforehand), block j descending: x_j = X_j^T w_j, then
+// w_c -= sum_r L[j0+r][c] x_j[r] for every column c left of the block. One small grid per block; every CTA
+// recomputes the 64x64 mat-vec x_j (4096 FMAs) instead of synchronising on it.
+__global__ void __launch_bounds__(256) ldl_back_kernel(const double *A, int n, int j0, int nbw, const double *Xcm,
+                                                       double *sol, double *x) {
+  __shared__ double wj[NB], xj[NB];
+  const int tid = threadIdx.x;
+  if (tid < NB) wj[tid] = tid < nbw ? sol[j0 + tid] : 0.0;
+  __syncthreads();
+  if (tid < NB) {  // x_j[c] = sum_r X[r][c] w[r], X column-major: contiguous in r
+    double s = 0.0;
+    const double *xc = Xcm + tid * NB;
+#pragma unroll 8
+    for (int r = 0; r < NB; r++) s += xc[r] * wj[r];
+    xj[tid] = s;
+    if (blockIdx.x == 0 && tid < nbw) x[j0 + tid] = s;
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + tid;
+  if (c < j0) {
+    const double *col = A + (size_t)c * n + j0;
+    double s = 0.0;
+    for (int r = 0; r < nbw; r++) s += col[r] * xj[r];
+    sol[c] -= s;
+  }
+}
+
+__global__ void scale_rhs_kernel(double *sol, const double *dinv_all, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sol[i] *= dinv_all[i];
+}
+
+__global__ void __launch_bounds__(1024) q1_kernel(const double *x, const double *g, const double *dvec, int n,
+                                                  const double *u_dev, double *scal) {
   __shared__ double red[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < n; i += 1024) sx[i] = -g[i];
-  __syncthreads();
-  // forward: L y = b (unit lower), column-oriented by blocks
-  for (int j0 = 0; j0 < n; j0 += NB) {
-    const int nbw = (n - j0 < NB) ? n - j0 : NB;
-    if (warp == 0) {
-      for (int c = 0; c < nbw; c++) {
-        const double yc = sx[j0 + c];
-        for (int r = c + 1 + lane; r < nbw; r += 32) sx[j0 + r] -= A[(size_t)(j0 + c) * n + j0 + r] * yc;
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    if (tid < nbw) sblk[tid] = sx[j0 + tid];
-    __syncthreads();
-    for (int i = j0 + nbw + tid; i < n; i += 1024) {
-      double s = sx[i];
-      for (int c = 0; c < nbw; c++) s -= A[(size_t)(j0 + c) * n + i] * sblk[c];
-      sx[i] = s;
-    }
-    __syncthreads();
-  }
-  for (int i = tid; i < n; i += 1024) sx[i] /= A[(size_t)i * n + i];
-  __syncthreads();
-  // backward: L^T x = z
-  const int nblk = (n + NB - 1) / NB;
-  for (int b = nblk - 1; b >= 0; b--) {
-    const int j0 = b * NB;
-    const int nbw = (n - j0 < NB) ? n - j0 : NB;
-    // s_c = sum_{i >= j0+nbw} L[i][j0+c] x_i : one warp per column (32 warps, two rounds for 64 columns)
-    for (int c = warp; c < nbw; c += 32) {
-      double s = 0.0;
-      const double *col = A + (size_t)(j0 + c) * n;
-      for (int i = j0 + nbw + lane; i < n; i += 32) s += col[i] * sx[i];
-      s = warp_sum(s);
-      if (lane == 0) sblk[c] = s;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      for (int c = lane; c < nbw; c += 32) sx[j0 + c] -= sblk[c];
-      __syncwarp();
-      for (int c = nbw - 1; c >= 0; c--) {
-        // x_c final; eliminate it from rows above inside the block: x_r -= L[c][r] * x_c for r < c
-        const double xc = sx[j0 + c];
-        for (int r = lane; r < c; r += 32) sx[j0 + r] -= A[(size_t)(j0 + r) * n + j0 + c] * xc;
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-  }
+  const double u = *u_dev;
   double part = 0.0;
   for (int i = tid; i < n; i += 1024) {
-    const double xi = sx[i];
-    x[i] = xi;
+    const double xi = x[i];
     part += xi * (u * dvec[i] * xi - g[i]);
   }
   part = warp_sum(part);
@@ -202,7 +276,7 @@ __global__ void __launch_bounds__(1024) ldl_solve_kernel(const double *A, const 
   if (warp == 0) {
     double s = red[lane];
     s = warp_sum(s);
-    if (lane == 0) scal[1] = 0.5 * s;  // q1
+    if (lane == 0) scal[1] = 0.5 * s;  // q1 = 0.5 dx.(u D dx - g)  (bavoxel.hpp:1127)
   }
 }
 
@@ -256,45 +330,81 @@ __global__ void gauge_kernel(double *poses, const double *pose0_snapshot, int N,
 
 }  // namespace
 
-int launch_ldlt_solve(balm_ctx *c, double u) {
+static int enqueue_solve(balm_ctx *c) {
   const int n = c->n;
-  CUDA_TRY(cudaMemsetAsync(c->flags, 0, sizeof(int) * 4, c->stream));
+  cudaStream_t st = c->stream;
   dim3 g1((n + 255) / 256, n);
-  damp_copy_kernel<<<g1, 256, 0, c->stream>>>(c->H, c->A, c->dvec, n, u);
-  c->launches += 1;
-  const int panel_smem = (2 * NB * (NB + 1) + NB) * (int)sizeof(double);
-  const int update_smem = 2 * NB * (NB + 1) * (int)sizeof(double);
-  static bool attr_set2 = false;
-  if (!attr_set2) {
-    CUDA_TRY(cudaFuncSetAttribute(ldl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
-    CUDA_TRY(cudaFuncSetAttribute(ldl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, update_smem));
-    attr_set2 = true;
-  }
-  for (int j0 = 0; j0 < n; j0 += NB) {
+  damp_copy_kernel<<<g1, 256, 0, st>>>(c->H, c->A, c->dvec, n, c->scal + 3);
+  rhs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->g, c->sol, n);
+  const int panel_smem = 2 * NB * (NB + 4) * (int)sizeof(double);
+  const int update_smem = 2 * UK * (UT + 4) * (int)sizeof(double);
+  int launches = 2;
+  for (int j0 = 0, pi = 0; j0 < n; j0 += NB, pi++) {
     const int nbw = (n - j0 < NB) ? n - j0 : NB;
-    ldl_diag_kernel<<<1, 256, 0, c->stream>>>(c->A, n, j0, nbw, c->flags);
-    c->launches += 1;
+    double *X = c->Xinv + (size_t)pi * NB * NB;
+    ldl_diag_kernel<<<1, 256, 0, st>>>(c->A, n, j0, nbw, X, c->dinv, c->sol, c->flags);
+    launches++;
     const int m = n - j0 - nbw;
     if (m > 0) {
-      const int mt = (m + NB - 1) / NB;
-      ldl_panel_kernel<<<mt, NB, panel_smem, c->stream>>>(c->A, c->W, n, j0, nbw);
-      ldl_update_kernel<<<mt * (mt + 1) / 2, 256, update_smem, c->stream>>>(c->A, c->W, n, j0, nbw);
-      c->launches += 2;
+      const int mt = (m + NB - 1) / NB, mu = (m + UT - 1) / UT;
+      ldl_panel_kernel<<<mt, 256, panel_smem, st>>>(c->A, c->W, n, j0, nbw, X, c->dinv, c->sol);
+      ldl_update_kernel<<<mu * (mu + 1) / 2, 256, update_smem, st>>>(c->A, c->W, n, j0, nbw);
+      launches += 2;
     }
   }
-  static bool attr_set = false;
-  const int smem = n * (int)sizeof(double);
-  if (!attr_set && smem > 48 * 1024) {
-    CUDA_TRY(cudaFuncSetAttribute(ldl_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  scale_rhs_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->sol, c->dinv, n);
+  launches++;
+  const int npan = (n + NB - 1) / NB;
+  for (int pi = npan - 1; pi >= 0; pi--) {
+    const int j0 = pi * NB;
+    const int nbw = (n - j0 < NB) ? n - j0 : NB;
+    const int blocks = j0 > 0 ? (j0 + 255) / 256 : 1;
+    ldl_back_kernel<<<blocks, 256, 0, st>>>(c->A, n, j0, nbw, c->Xinv + (size_t)pi * NB * NB, c->sol, c->dx);
+    launches++;
   }
-  if (smem > 200 * 1024) {
-    balm_set_error("n too large for the single-CTA triangular solve (n <= 25600)");
-    return BALM_ERR_UNSUPPORTED;
+  q1_kernel<<<1, 1024, 0, st>>>(c->dx, c->g, c->dvec, n, c->scal + 3, c->scal);
+  launches++;
+  c->solve_launches = launches;
+  return BALM_OK;
+}
+
+int launch_ldlt_solve(balm_ctx *c, double u) {
+  const int n = c->n;
+  static bool attr_set2 = false;
+  if (!attr_set2) {
+    CUDA_TRY(cudaFuncSetAttribute(ldl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  2 * NB * (NB + 4) * (int)sizeof(double)));
+    CUDA_TRY(cudaFuncSetAttribute(ldl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  2 * UK * (UT + 4) * (int)sizeof(double)));
+    attr_set2 = true;
   }
-  ldl_solve_kernel<<<1, 1024, smem, c->stream>>>(c->A, c->g, c->dvec, c->dx, n, u, c->scal);
-  c->launches += 1;
-  CUDA_TRY(cudaGetLastError());
+  if (!c->Xinv) {
+    const int npan = (n + NB - 1) / NB;
+    CUDA_TRY(cudaMalloc((void **)&c->Xinv, sizeof(double) * (size_t)npan * NB * NB));
+    CUDA_TRY(cudaMalloc((void **)&c->dinv, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc((void **)&c->sol, sizeof(double) * n));
+  }
+  c->h_scal[3] = u;  // pinned; the kernels read the damping factor from device memory so the graph is reusable
+  CUDA_TRY(cudaMemcpyAsync(c->scal + 3, c->h_scal + 3, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->flags, 0, sizeof(int) * 4, c->stream));
+  static const bool use_graph = getenv("BALM_NO_GRAPH") == nullptr;
+  if (!use_graph) {
+    TRY_LAUNCH(enqueue_solve(c));
+    c->launches += c->solve_launches;
+    CUDA_TRY(cudaGetLastError());
+    return BALM_OK;
+  }
+  if (!c->solve_graph) {  // capture the ~190-launch sequence once, replay it with one launch afterwards
+    cudaGraph_t graph;
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_solve(c);
+    CUDA_TRY(cudaStreamEndCapture(c->stream, &graph));
+    if (rc != BALM_OK) return rc;
+    CUDA_TRY(cudaGraphInstantiate((cudaGraphExec_t *)&c->solve_graph, graph, 0));
+    CUDA_TRY(cudaGraphDestroy(graph));
+  }
+  CUDA_TRY(cudaGraphLaunch((cudaGraphExec_t)c->solve_graph, c->stream));
+  c->launches += c->solve_launches;
   return BALM_OK;
 }
 
