@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0,
       __syncthreads();
       const double d = colA[buf][j];
       if (!(fabs(d) > 1e-290 && fabs(d) < 1e300)) bad = true;
-      const double dinv = 1.0 / d;
+      const double dinv = __drcp_rn(d);  // correctly rounded reciprocal, far shorter than the IEEE division path
       double lr[4], cc[4], xr[4];
 #pragma unroll
       for (int p = 0; p < 4; p++) lr[p] = colA[buf][4 * tx + p] * dinv;  // L[r][j]
@@ -127,10 +127,21 @@ __global__ void __launch_bounds__(256) ldl_panel_kernel(double *A, double *W, in
   __shared__ double yj[NB], dv[NB];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int i0 = j0 + nbw + blockIdx.x * NB;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e & (NB - 1), k = e >> 6;
-    sA[k][r] = (k < nbw && i0 + r < n) ? A[(size_t)(j0 + k) * n + i0 + r] : 0.0;
-    sX[k][r] = Xcm[k * NB + r];  // X[r][k]
+  {
+    // all 32 loads of this thread are issued before the first shared-memory store (latency paid once)
+    double ra[16], rx[16];
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+      const int e = tid + it * 256, r = e & (NB - 1), k = e >> 6;
+      ra[it] = (k < nbw && i0 + r < n) ? A[(size_t)(j0 + k) * n + i0 + r] : 0.0;
+      rx[it] = Xcm[k * NB + r];  // X[r][k]
+    }
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+      const int e = tid + it * 256, r = e & (NB - 1), k = e >> 6;
+      sA[k][r] = ra[it];
+      sX[k][r] = rx[it];
+    }
   }
   if (tid < NB) {
     yj[tid] = tid < nbw ? sol[j0 + tid] : 0.0;
@@ -172,6 +183,11 @@ __global__ void __launch_bounds__(256) ldl_panel_kernel(double *A, double *W, in
   }
 }
 
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+
 constexpr int UT = 128;  // update tile
 constexpr int UK = 32;   // k chunk
 __global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double *W, int n, int j0, int nbw) {
@@ -187,12 +203,18 @@ __global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double
   double acc[8][8] = {};
   for (int k0 = 0; k0 < nbw; k0 += UK) {
     __syncthreads();
-    for (int e = tid; e < UK * UT; e += 256) {
-      const int rr = e & (UT - 1), k = e >> 7;
+    // 16-byte cp.async pieces (n, r0, c0 are even, so a pair is entirely inside or outside the matrix)
+#pragma unroll
+    for (int it = 0; it < (UK * UT / 2) / 256; it++) {
+      const int e = tid + it * 256, rr = (e & (UT / 2 - 1)) * 2, k = e >> 6;
       const bool kv = k0 + k < nbw;
-      sL[k][rr] = (kv && r0 + rr < n) ? A[(size_t)(j0 + k0 + k) * n + r0 + rr] : 0.0;
-      sW[k][rr] = (kv && c0 + rr < n) ? W[(size_t)(k0 + k) * n + c0 + rr] : 0.0;
+      if (kv && r0 + rr < n) cp_async16(&sL[k][rr], A + (size_t)(j0 + k0 + k) * n + r0 + rr);
+      else *reinterpret_cast<double2 *>(&sL[k][rr]) = make_double2(0.0, 0.0);
+      if (kv && c0 + rr < n) cp_async16(&sW[k][rr], W + (size_t)(k0 + k) * n + c0 + rr);
+      else *reinterpret_cast<double2 *>(&sW[k][rr]) = make_double2(0.0, 0.0);
     }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
 #pragma unroll 4
     for (int k = 0; k < UK; k++) {
@@ -246,12 +268,15 @@ __global__ void __launch_bounds__(256) ldl_back_kernel(const double *A, int n, i
     if (blockIdx.x == 0 && tid < nbw) x[j0 + tid] = s;
   }
   __syncthreads();
-  const int c = blockIdx.x * 256 + tid;
-  if (c < j0) {
+  // one warp per column: the 64 contiguous doubles L[j0..j0+63][c] are one coalesced 512-byte request
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int c = (blockIdx.x * 8 + warp) * 4; c < j0 && c < (blockIdx.x * 8 + warp) * 4 + 4; c++) {
     const double *col = A + (size_t)c * n + j0;
     double s = 0.0;
-    for (int r = 0; r < nbw; r++) s += col[r] * xj[r];
-    sol[c] -= s;
+    if (lane < nbw) s = col[lane] * xj[lane];
+    if (lane + 32 < nbw) s += col[lane + 32] * xj[lane + 32];
+    s = warp_sum(s);
+    if (lane == 0) sol[c] -= s;
   }
 }
 
@@ -358,7 +383,7 @@ static int enqueue_solve(balm_ctx *c) {
   for (int pi = npan - 1; pi >= 0; pi--) {
     const int j0 = pi * NB;
     const int nbw = (n - j0 < NB) ? n - j0 : NB;
-    const int blocks = j0 > 0 ? (j0 + 255) / 256 : 1;
+    const int blocks = j0 > 0 ? (j0 + 31) / 32 : 1;
     ldl_back_kernel<<<blocks, 256, 0, st>>>(c->A, n, j0, nbw, c->Xinv + (size_t)pi * NB * NB, c->sol, c->dx);
     launches++;
   }
