@@ -94,8 +94,10 @@ static int alloc_workspaces(balm_ctx *c) {
   }
   c->VB = vb;
   TRY(dev_alloc(&c->stats, (size_t)vb * BALM_STATS_STRIDE));
-  TRY(dev_alloc(&c->G, (size_t)3 * vb * c->ldg));
-  CUDA_TRY(cudaMemsetAsync(c->G, 0, sizeof(double) * (size_t)3 * vb * c->ldg, c->stream));  // zero the column padding
+  if (c->prec == BALM_PREC_FP64) {  // the tensor path writes int8 digit planes directly and never stores fp64 G'
+    TRY(dev_alloc(&c->G, (size_t)3 * vb * c->ldg));
+    CUDA_TRY(cudaMemsetAsync(c->G, 0, sizeof(double) * (size_t)3 * vb * c->ldg, c->stream));  // zero the column padding
+  }
   const int tiles_p = (c->N + 31) / 32;
   c->obs_chunks = std::max(1, (c->sm_count * 16 + tiles_p - 1) / tiles_p);
   if (c->obs_chunks > 4096) c->obs_chunks = 4096;
@@ -373,22 +375,19 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     TRY(launch_voxel_stats(c, poses, v0, v1, true, include_fix, r_dev));
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    if (c->prec == BALM_PREC_TENSOR) TRY(tensor_syrk_prepare(c));
-    TRY(launch_obs_pass(c, poses, v0, v1, first));
-    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-    if (c->prec == BALM_PREC_TENSOR) TRY(launch_tensor_syrk(c, 3 * (v1 - v0), first));
-    else TRY(launch_syrk_f64(c, 3 * (v1 - v0), first));
+    if (c->prec == BALM_PREC_TENSOR) {
+      TRY(tensor_obs_and_syrk(c, poses, v0, v1, first));  // records ev[2] between the sweeps and the SYRK
+    } else {
+      TRY(launch_obs_pass(c, poses, v0, v1, first));
+      CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+      TRY(launch_syrk_f64(c, 3 * (v1 - v0), first));
+    }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     CUDA_TRY(cudaEventSynchronize(c->ev[3]));
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->tm.ms_stats += ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->tm.ms_obs += ms;
-    if (c->prec == BALM_PREC_TENSOR) {
-      cudaEventElapsedTime(&ms, c->ev[2], c->ev[12]); c->tm.ms_slice += ms;
-      cudaEventElapsedTime(&ms, c->ev[12], c->ev[3]); c->tm.ms_syrk += ms;
-      TRY(tensor_syrk_check(c));
-    } else {
-      cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->tm.ms_syrk += ms;
-    }
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->tm.ms_syrk += ms;
+    if (c->prec == BALM_PREC_TENSOR) TRY(tensor_syrk_check(c));
     first = false;
   }
   CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));

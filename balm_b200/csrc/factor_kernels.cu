@@ -31,72 +31,70 @@ struct StatsArgs {
   double *res_part;   // [gridDim.x]
 };
 
+// One WARP per voxel: no block barriers, every warp is an independent stream of (loads -> shuffle reduce -> eig),
+// so the serial eigen-solve of one voxel overlaps the loads of the others. Lanes stride over the voxel's
+// observations with two observations (20 independent 8-byte loads) in flight per lane.
+constexpr int STATS_WARPS = STATS_THREADS / 32;
 template <bool STORE>
 __global__ void __launch_bounds__(STATS_THREADS) voxel_stats_kernel(StatsArgs a) {
-  __shared__ double red[STATS_THREADS / 32][10];
-  __shared__ double tot[10];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double res_acc = 0.0;  // meaningful in warp 0 only (all lanes hold the same value)
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * STATS_WARPS + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * STATS_WARPS;
+  double res_acc = 0.0;
 
-  for (int64_t v = a.v0 + blockIdx.x; v < a.v1; v += gridDim.x) {
+  for (int64_t v = a.v0 + gw; v < a.v1; v += nw) {
     const long long s0 = a.row_ptr[v];
     const int k = (int)(a.row_ptr[v + 1] - s0);
     double acc[10];
 #pragma unroll
     for (int c = 0; c < 10; c++) acc[c] = 0.0;
-    for (int j = tid; j < k; j += STATS_THREADS) {
-      const long long s = s0 + j;
-      double o[10];
+    for (int j = lane; j < k; j += 64) {
+      const long long sA = s0 + j;
+      const bool hasB = j + 32 < k;
+      const long long sB = hasB ? sA + 32 : sA;
+      double oa[10], ob[10];
 #pragma unroll
-      for (int c = 0; c < 10; c++) o[c] = __ldg(a.obs + c * a.Kp + s);
-      const int pid = __ldg(a.pose_idx + s);
+      for (int c = 0; c < 10; c++) { oa[c] = __ldg(a.obs + c * a.Kp + sA); ob[c] = __ldg(a.obs + c * a.Kp + sB); }
+      const int pa = __ldg(a.pose_idx + sA), pb = __ldg(a.pose_idx + sB);
       double r[9], p[3];
-      load_pose(a.poses + 12 * pid, r, p);
-      const WC w = world_cluster(o, r, p);
+      load_pose(a.poses + 12 * pa, r, p);
+      WC w = world_cluster(oa, r, p);
       acc[0] += w.p00; acc[1] += w.p01; acc[2] += w.p02; acc[3] += w.p11; acc[4] += w.p12;
       acc[5] += w.p22; acc[6] += w.v0;  acc[7] += w.v1;  acc[8] += w.v2;  acc[9] += w.n;
-    }
-#pragma unroll
-    for (int c = 0; c < 10; c++) acc[c] = warp_sum(acc[c]);
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < 10; c++) red[warp][c] = acc[c];
-    }
-    __syncthreads();
-    if (warp == 0) {
-      if (lane < 10) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < STATS_THREADS / 32; w++) t += red[w][lane];
-        if (a.fix) t += __ldg(a.fix + lane * a.M + v);
-        tot[lane] = t;
-      }
-      __syncwarp();
-      const double NN = tot[9];
-      const double inv = 1.0 / NN;
-      const double vb0 = tot[6] * inv, vb1 = tot[7] * inv, vb2 = tot[8] * inv;
-      double lam[3], u0[3], u1[3], u2[3];
-      eig3_jacobi(tot[0] * inv - vb0 * vb0, tot[1] * inv - vb0 * vb1, tot[2] * inv - vb0 * vb2,
-                  tot[3] * inv - vb1 * vb1, tot[4] * inv - vb1 * vb2, tot[5] * inv - vb2 * vb2, lam, u0, u1, u2);
-      const double coe = __ldg(a.coe + v);
-      res_acc += coe * lam[0];
-      if (STORE && lane == 0) {
-        double *st = a.stats + (v - a.v0) * BALM_STATS_STRIDE;
-        st[0] = vb0; st[1] = vb1; st[2] = vb2;
-        st[3] = u0[0]; st[4] = u0[1]; st[5] = u0[2];
-        st[6] = u1[0]; st[7] = u1[1]; st[8] = u1[2];
-        st[9] = u2[0]; st[10] = u2[1]; st[11] = u2[2];
-        st[12] = inv;
-        st[13] = sqrt(2.0 * coe) * inv;               // sqrt(coe*|w0|), w0 = -2/NN^2 (bavoxel.hpp:385)
-        st[14] = sqrt(2.0 * coe / (lam[1] - lam[0])); // sqrt(coe*|w1|), w1 = 2/(l0-l1) (bavoxel.hpp:392)
-        st[15] = sqrt(2.0 * coe / (lam[2] - lam[0]));
-        st[16] = coe;
-        st[17] = lam[0]; st[18] = lam[1]; st[19] = lam[2];
+      if (hasB) {
+        load_pose(a.poses + 12 * pb, r, p);
+        w = world_cluster(ob, r, p);
+        acc[0] += w.p00; acc[1] += w.p01; acc[2] += w.p02; acc[3] += w.p11; acc[4] += w.p12;
+        acc[5] += w.p22; acc[6] += w.v0;  acc[7] += w.v1;  acc[8] += w.v2;  acc[9] += w.n;
       }
     }
-    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 10; c++) {
+      acc[c] = warp_sum(acc[c]);
+      if (a.fix) acc[c] += __ldg(a.fix + c * a.M + v);
+    }
+    const double inv = 1.0 / acc[9];
+    const double vb0 = acc[6] * inv, vb1 = acc[7] * inv, vb2 = acc[8] * inv;
+    double lam[3], u0[3], u1[3], u2[3];
+    eig3_jacobi(acc[0] * inv - vb0 * vb0, acc[1] * inv - vb0 * vb1, acc[2] * inv - vb0 * vb2,
+                acc[3] * inv - vb1 * vb1, acc[4] * inv - vb1 * vb2, acc[5] * inv - vb2 * vb2, lam, u0, u1, u2);
+    const double coe = __ldg(a.coe + v);
+    res_acc += coe * lam[0];
+    if (STORE && lane == 0) {
+      double *st = a.stats + (v - a.v0) * BALM_STATS_STRIDE;
+      st[0] = vb0; st[1] = vb1; st[2] = vb2;
+      st[3] = u0[0]; st[4] = u0[1]; st[5] = u0[2];
+      st[6] = u1[0]; st[7] = u1[1]; st[8] = u1[2];
+      st[9] = u2[0]; st[10] = u2[1]; st[11] = u2[2];
+      st[12] = inv;
+      st[13] = sqrt(2.0 * coe) * inv;               // sqrt(coe*|w0|), w0 = -2/NN^2 (bavoxel.hpp:385)
+      st[14] = sqrt(2.0 * coe / (lam[1] - lam[0])); // sqrt(coe*|w1|), w1 = 2/(l0-l1) (bavoxel.hpp:392)
+      st[15] = sqrt(2.0 * coe / (lam[2] - lam[0]));
+      st[16] = coe;
+      st[17] = lam[0]; st[18] = lam[1]; st[19] = lam[2];
+    }
   }
-  if (tid == 0) a.res_part[blockIdx.x] = res_acc;
+  if (lane == 0) a.res_part[gw] = res_acc;
 }
 
 // deterministic sum of the per-CTA residual partials (single warp)
@@ -119,13 +117,23 @@ struct ObsArgs {
   double *G;            // [3*(v1-v0)][ldg]
   double *part;         // [chunks][27][Np]
   unsigned long long *colmax;  // [ldg] or null: running max |G'[:,j]| (tensor path column scales)
+  // tensor path, digit-plane output (OBS_INT8)
+  const double *sc;     // [ldg] column scales 2^p
+  int8_t *Gq;           // [S][rows_alloc][ldg]
+  int64_t plane_stride;
+  int S;
   // csc
   const int *csc_ptr, *csc_obs, *csc_vox;
 };
 
 // One lane = one pose; a warp covers 32 consecutive poses and walks a chunk of voxels, so the observation
 // loads of a dense scene (slot j == pose j) are coalesced and the 27 accumulators stay in registers.
-template <bool DENSE>
+enum { OBS_FP64 = 0, OBS_MAXONLY = 1, OBS_INT8 = 2 };
+// MODE: OBS_FP64    writes fp64 G' (+ gradient / diagonal blocks)            [fp64 SYRK path]
+//       OBS_MAXONLY only the column maxima of G' (first sweep of the tensor path -> power-of-two column scales)
+//       OBS_INT8    writes the balanced base-256 digit planes of rint(G' * sc) directly (+ gradient / blocks),
+//                   so the tensor path never materialises G' in fp64
+template <bool DENSE, int MODE>
 __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile = blockIdx.y * 4 + warp;
@@ -138,6 +146,11 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
 #pragma unroll
   for (int q = 0; q < BALM_ACC; q++) acc[q] = 0.0;
   double cmax[6] = {0, 0, 0, 0, 0, 0};
+  double scl[6] = {0, 0, 0, 0, 0, 0};
+  if (MODE == OBS_INT8 && active) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) scl[q] = __ldg(a.sc + 6 * i + q);
+  }
 
   long long t0, t1;
   if (DENSE) {
@@ -149,19 +162,33 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
     t1 = t0 + a.chunk < e ? t0 + a.chunk : e;
   }
 
-  for (long long t = t0; t < t1; t++) {
-    long long s, v;
-    if (DENSE) {
-      v = t;
-      s = __ldg(a.row_ptr + v) + i;
-      if (!active) continue;
-    } else {
-      s = a.csc_obs[t];
-      v = a.csc_vox[t];
+  // software prefetch: the ten observation words of iteration t+1 are requested before iteration t is computed,
+  // so one global-memory round trip is always in flight per warp (dense scenes: s = v*N + i, no index loads)
+  double onext[10];
+  auto issue = [&](long long t, double *dst) {
+    if (t < t1) {
+      long long s;
+      if (DENSE) s = t * (long long)a.N + i;
+      else s = a.csc_obs[t];
+      if (!DENSE || active) {
+#pragma unroll
+        for (int c = 0; c < 10; c++) dst[c] = __ldg(a.obs + c * a.Kp + s);
+      }
     }
+  };
+  issue(t0, onext);
+  for (long long t = t0; t < t1; t++) {
+    long long v;
     double o[10];
 #pragma unroll
-    for (int c = 0; c < 10; c++) o[c] = __ldg(a.obs + c * a.Kp + s);
+    for (int c = 0; c < 10; c++) o[c] = onext[c];
+    issue(t + 1, onext);
+    if (DENSE) {
+      v = t;
+      if (!active) continue;
+    } else {
+      v = a.csc_vox[t];
+    }
     const double2 *st2 = reinterpret_cast<const double2 *>(a.stats + (v - a.v0) * BALM_STATS_STRIDE);
     double st[BALM_STATS_STRIDE];
 #pragma unroll
@@ -206,23 +233,49 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
     cross3(u0, vw, cuv);
     const double ai[6] = {-cuv[0], -cuv[1], -cuv[2], w.n * u0[0], w.n * u0[1], w.n * u0[2]};
 
-    // ---- G' rows (3 per voxel), 6 contiguous doubles per pose ----
+    // ---- G' rows (3 per voxel), 6 contiguous values per pose ----
     {
-      double *g0 = a.G + (size_t)(3 * (v - a.v0)) * a.ldg + 6 * i;
       const double c0 = st[13], c1s = st[14], c2s = st[15];
-      double2 *q0 = reinterpret_cast<double2 *>(g0);
-      double2 *q1 = reinterpret_cast<double2 *>(g0 + a.ldg);
-      double2 *q2 = reinterpret_cast<double2 *>(g0 + 2 * (size_t)a.ldg);
+      double gv[3][6];
 #pragma unroll
-      for (int h = 0; h < 3; h++) {
-        q0[h] = make_double2(c0 * ai[2 * h], c0 * ai[2 * h + 1]);
-        q1[h] = make_double2(c1s * gk[1][2 * h], c1s * gk[1][2 * h + 1]);
-        q2[h] = make_double2(c2s * gk[2][2 * h], c2s * gk[2][2 * h + 1]);
+      for (int q = 0; q < 6; q++) { gv[0][q] = c0 * ai[q]; gv[1][q] = c1s * gk[1][q]; gv[2][q] = c2s * gk[2][q]; }
+      if (MODE == OBS_FP64) {
+        double *g0 = a.G + (size_t)(3 * (v - a.v0)) * a.ldg + 6 * i;
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+          double2 *qd = reinterpret_cast<double2 *>(g0 + (size_t)rr * a.ldg);
+#pragma unroll
+          for (int h = 0; h < 3; h++) qd[h] = make_double2(gv[rr][2 * h], gv[rr][2 * h + 1]);
+        }
       }
+      if (MODE == OBS_INT8) {
+        // |G' * sc| < 2^30, so X fits an int32 and ALL its balanced base-256 digits d_k in [-128,127] fall out of
+        // two integer ops: the unsigned bytes of X + 0x80808080 are d_k + 128, and xor 0x80 turns them into int8.
 #pragma unroll
-      for (int q = 0; q < 6; q++)
-        cmax[q] = fmax(cmax[q], fmax(fabs(c0 * ai[q]), fmax(fabs(c1s * gk[1][q]), fabs(c2s * gk[2][q]))));
+        for (int rr = 0; rr < 3; rr++) {
+          unsigned D[6];
+#pragma unroll
+          for (int q = 0; q < 6; q++)
+            D[q] = ((unsigned)__double2int_rn(gv[rr][q] * scl[q]) + 0x80808080u) ^ 0x80808080u;
+          int8_t *base = a.Gq + (size_t)(3 * (v - a.v0) + rr) * a.ldg + 6 * i;
+#pragma unroll
+          for (int kb = 0; kb < 4; kb++) {        // byte kb = digit of weight 256^kb = plane S-1-kb
+            if (kb < a.S) {
+              unsigned short *o16 = reinterpret_cast<unsigned short *>(base + (size_t)(a.S - 1 - kb) * a.plane_stride);
+#pragma unroll
+              for (int h = 0; h < 3; h++)
+                o16[h] = (unsigned short)__byte_perm(D[2 * h], D[2 * h + 1], kb | ((4 + kb) << 4));
+            }
+          }
+        }
+      }
+      if (MODE != OBS_INT8) {
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+          cmax[q] = fmax(cmax[q], fmax(fabs(gv[0][q]), fmax(fabs(gv[1][q]), fabs(gv[2][q]))));
+      }
     }
+    if (MODE == OBS_MAXONLY) continue;
     // ---- gradient (bavoxel.hpp:381) ----
 #pragma unroll
     for (int q = 0; q < 6; q++) acc[q] += coe * gk[0][q];
@@ -265,12 +318,12 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
       }
     }
   }
-  if (active && a.colmax) {
+  if (MODE != OBS_INT8 && active && a.colmax) {
 #pragma unroll
     for (int q = 0; q < 6; q++)  // non-negative doubles order like their bit patterns
       atomicMax(a.colmax + 6 * i + q, (unsigned long long)__double_as_longlong(cmax[q]));
   }
-  if (active) {
+  if (MODE != OBS_MAXONLY && active) {
     double *pp = a.part + (size_t)blockIdx.x * BALM_ACC * a.Np + i;
 #pragma unroll
     for (int q = 0; q < BALM_ACC; q++) pp[(size_t)q * a.Np] = acc[q];
@@ -292,42 +345,100 @@ int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1,
   // residual_out_dev: accumulated (+=) when it is not the first batch -> caller zeroes it first
   const int64_t nv = v1 - v0;
   if (nv <= 0) return BALM_OK;
-  int blocks = (int)(nv < (int64_t)c->res_blocks ? nv : c->res_blocks);
+  const int64_t want = (nv + STATS_WARPS - 1) / STATS_WARPS;
+  const int max_blocks = c->res_blocks / STATS_WARPS;
+  int blocks = (int)(want < (int64_t)max_blocks ? want : max_blocks);
   StatsArgs a{c->obs, c->Kp, c->pose_idx, c->row_ptr, c->coe, use_fix ? c->fix : nullptr, c->M, poses, v0, v1,
               store_stats ? c->stats : nullptr, c->res_part};
   if (store_stats) voxel_stats_kernel<true><<<blocks, STATS_THREADS, 0, c->stream>>>(a);
   else voxel_stats_kernel<false><<<blocks, STATS_THREADS, 0, c->stream>>>(a);
-  residual_reduce_kernel<<<1, 32, 0, c->stream>>>(c->res_part, blocks, residual_out_dev, 1);
+  residual_reduce_kernel<<<1, 32, 0, c->stream>>>(c->res_part, blocks * STATS_WARPS, residual_out_dev, 1);
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return BALM_OK;
 }
 
-int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch) {
-  const int64_t nv = v1 - v0;
-  if (nv <= 0) return BALM_OK;
+static int obs_grid(balm_ctx *c, ObsArgs &a, int64_t nv, dim3 &grid) {
   const int tiles = (c->N + 31) / 32;
-  ObsArgs a{};
-  a.obs = c->obs; a.Kp = c->Kp; a.row_ptr = c->row_ptr; a.poses = poses; a.stats = c->stats;
-  a.v0 = v0; a.v1 = v1; a.N = c->N; a.Np = c->Np; a.ldg = c->ldg; a.G = c->G; a.part = c->obs_part;
-  a.csc_ptr = c->csc_ptr; a.csc_obs = c->csc_obs; a.csc_vox = c->csc_vox;
-  a.colmax = c->colmax;
   int chunks;
   if (c->dense) {
     chunks = (int)(nv < (int64_t)c->obs_chunks ? nv : c->obs_chunks);
     a.chunk = (int)((nv + chunks - 1) / chunks);
     chunks = (int)((nv + a.chunk - 1) / a.chunk);
   } else {
-    // sparse: G' rows of non-observing poses must be zero
-    CUDA_TRY(cudaMemsetAsync(c->G, 0, sizeof(double) * (size_t)3 * nv * c->ldg, c->stream));
     const int len = c->csc_max_len > 0 ? c->csc_max_len : 1;
     chunks = len < c->obs_chunks ? len : c->obs_chunks;
     a.chunk = (len + chunks - 1) / chunks;
     chunks = (len + a.chunk - 1) / a.chunk;
   }
-  dim3 grid(chunks, (tiles + 3) / 4);
-  if (c->dense) obs_pass_kernel<true><<<grid, 128, 0, c->stream>>>(a);
-  else obs_pass_kernel<false><<<grid, 128, 0, c->stream>>>(a);
+  grid = dim3(chunks, (tiles + 3) / 4);
+  return chunks;
+}
+
+static void obs_fill(balm_ctx *c, ObsArgs &a, const double *poses, int64_t v0, int64_t v1) {
+  a = ObsArgs{};
+  a.obs = c->obs; a.Kp = c->Kp; a.row_ptr = c->row_ptr; a.poses = poses; a.stats = c->stats;
+  a.v0 = v0; a.v1 = v1; a.N = c->N; a.Np = c->Np; a.ldg = c->ldg; a.G = c->G; a.part = c->obs_part;
+  a.csc_ptr = c->csc_ptr; a.csc_obs = c->csc_obs; a.csc_vox = c->csc_vox;
+  a.colmax = c->colmax;
+}
+
+// fp64 SYRK path: one sweep writing fp64 G' (+ gradient / diagonal blocks).
+int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch) {
+  const int64_t nv = v1 - v0;
+  if (nv <= 0) return BALM_OK;
+  ObsArgs a;
+  obs_fill(c, a, poses, v0, v1);
+  a.colmax = nullptr;
+  dim3 grid;
+  const int chunks = obs_grid(c, a, nv, grid);
+  if (!c->dense)  // sparse: G' rows of non-observing poses must be zero
+    CUDA_TRY(cudaMemsetAsync(c->G, 0, sizeof(double) * (size_t)3 * nv * c->ldg, c->stream));
+  if (c->dense) obs_pass_kernel<true, OBS_FP64><<<grid, 128, 0, c->stream>>>(a);
+  else obs_pass_kernel<false, OBS_FP64><<<grid, 128, 0, c->stream>>>(a);
+  const int total = BALM_ACC * c->Np;
+  obs_reduce_kernel<<<(total + 255) / 256, 256, 0, c->stream>>>(c->obs_part, chunks, total, c->accum,
+                                                                first_batch ? 0 : 1);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return BALM_OK;
+}
+
+// tensor path, sweep 1: column maxima of G' only.
+int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1) {
+  const int64_t nv = v1 - v0;
+  if (nv <= 0) return BALM_OK;
+  ObsArgs a;
+  obs_fill(c, a, poses, v0, v1);
+  dim3 grid;
+  obs_grid(c, a, nv, grid);
+  if (c->dense) obs_pass_kernel<true, OBS_MAXONLY><<<grid, 128, 0, c->stream>>>(a);
+  else obs_pass_kernel<false, OBS_MAXONLY><<<grid, 128, 0, c->stream>>>(a);
+  c->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BALM_OK;
+}
+
+// tensor path, sweep 2: int8 digit planes written directly (+ gradient / diagonal blocks).
+int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch, const double *sc,
+                    int8_t *Gq, int64_t plane_stride, int S, int64_t rows_padded) {
+  const int64_t nv = v1 - v0;
+  if (nv <= 0) return BALM_OK;
+  ObsArgs a;
+  obs_fill(c, a, poses, v0, v1);
+  a.sc = sc; a.Gq = Gq; a.plane_stride = plane_stride; a.S = S;
+  dim3 grid;
+  const int chunks = obs_grid(c, a, nv, grid);
+  if (!c->dense) {
+    for (int s = 0; s < S; s++)
+      CUDA_TRY(cudaMemsetAsync(Gq + (size_t)s * plane_stride, 0, (size_t)rows_padded * c->ldg, c->stream));
+  } else if (rows_padded > 3 * nv) {  // zero the K-padding rows of every plane
+    for (int s = 0; s < S; s++)
+      CUDA_TRY(cudaMemsetAsync(Gq + (size_t)s * plane_stride + (size_t)3 * nv * c->ldg, 0,
+                               (size_t)(rows_padded - 3 * nv) * c->ldg, c->stream));
+  }
+  if (c->dense) obs_pass_kernel<true, OBS_INT8><<<grid, 128, 0, c->stream>>>(a);
+  else obs_pass_kernel<false, OBS_INT8><<<grid, 128, 0, c->stream>>>(a);
   const int total = BALM_ACC * c->Np;
   obs_reduce_kernel<<<(total + 255) / 256, 256, 0, c->stream>>>(c->obs_part, chunks, total, c->accum,
                                                                 first_batch ? 0 : 1);

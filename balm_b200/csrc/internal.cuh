@@ -220,7 +220,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool store_stats, bool use_fix,
                        double *residual_out_dev);
 int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
-int launch_obs_reduce(balm_ctx *c);
+int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1);
+int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch, const double *sc,
+                    int8_t *Gq, int64_t plane_stride, int S, int64_t rows_padded);
+int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch);
 int launch_assemble(balm_ctx *c);
 int launch_ldlt_solve(balm_ctx *c, double u);
@@ -229,7 +232,5 @@ int launch_gauge(balm_ctx *c, double *poses, int mode);
 int launch_synth(balm_ctx *c, int64_t n_voxels, int64_t first_voxel, int pts, double noise, double range,
                  uint64_t seed, const double *poses_gt_dev);
 int tensor_syrk_init(balm_ctx *c);
-int launch_tensor_syrk(balm_ctx *c, int64_t rows, bool first_batch);
 void tensor_syrk_free(balm_ctx *c);
-int tensor_syrk_prepare(balm_ctx *c);
 int tensor_syrk_check(balm_ctx *c);

@@ -364,37 +364,6 @@ __global__ void tc_scale_kernel(const unsigned long long *colmax_bits, double *s
   isc[j] = ldexp(1.0, 8 * (S - 1) - p);
 }
 
-// fp64 G' -> S balanced base-256 digit planes (int8), 4 columns per thread
-__global__ void tc_slice_kernel(const double *G, int ldg, const double *sc, int8_t *Gq, int ldq, int64_t rows,
-                                int64_t rows_padded, int64_t plane_stride, int S) {
-  const int j = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
-  const int64_t c = blockIdx.x;
-  if (j >= ldq) return;
-  long long X[4] = {0, 0, 0, 0};
-  if (c < rows && j < ldg) {
-    const double2 g0 = *reinterpret_cast<const double2 *>(G + (size_t)c * ldg + j);
-    const double2 g1 = *reinterpret_cast<const double2 *>(G + (size_t)c * ldg + j + 2);
-    const double2 s0 = *reinterpret_cast<const double2 *>(sc + j);
-    const double2 s1 = *reinterpret_cast<const double2 *>(sc + j + 2);
-    X[0] = __double2ll_rn(g0.x * s0.x);
-    X[1] = __double2ll_rn(g0.y * s0.y);
-    X[2] = __double2ll_rn(g1.x * s1.x);
-    X[3] = __double2ll_rn(g1.y * s1.y);
-  }
-  for (int s = S - 1; s >= 0; s--) {  // least significant digit first
-    char4 out;
-    int8_t dd[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const long long dgt = ((X[q] + 128) & 255) - 128;
-      X[q] = (X[q] - dgt) >> 8;
-      dd[q] = (int8_t)dgt;
-    }
-    out.x = dd[0]; out.y = dd[1]; out.z = dd[2]; out.w = dd[3];
-    *reinterpret_cast<char4 *>(Gq + (size_t)s * plane_stride + (size_t)c * ldq + j) = out;
-  }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -422,6 +391,7 @@ int tensor_syrk_init(balm_ctx *c) {
   const int ldq = c->ldg;
   st->rows_alloc = (3 * c->VB + KS - 1) / KS * KS;
   CUDA_TRY(cudaMalloc((void **)&c->Gq, (size_t)st->S * st->rows_alloc * ldq));
+  CUDA_TRY(cudaMemset(c->Gq, 0, (size_t)st->S * st->rows_alloc * ldq));  // column padding [6N, ldg) stays zero
   CUDA_TRY(cudaMalloc((void **)&st->sc, sizeof(double) * ldq));
   CUDA_TRY(cudaMalloc((void **)&st->isc, sizeof(double) * ldq));
   CUDA_TRY(cudaMalloc((void **)&st->colmax, sizeof(unsigned long long) * ldq));
@@ -473,29 +443,28 @@ void tensor_syrk_free(balm_ctx *c) {
   c->colmax = nullptr;
 }
 
-int tensor_syrk_prepare(balm_ctx *c) {  // before the observation pass of a batch: reset the column maxima
-  TcState *st = static_cast<TcState *>(c->tmap);
-  CUDA_TRY(cudaMemsetAsync(st->colmax, 0, sizeof(unsigned long long) * c->ldg, c->stream));
-  return BALM_OK;
-}
-
-int launch_tensor_syrk(balm_ctx *c, int64_t rows, bool first_batch) {
+// One batch of the tensor path: (1) column maxima of G' -> power-of-two scales, (2) observation sweep writing the
+// int8 digit planes directly, (3) tcgen05 SYRK. ev[2] is recorded between the observation sweeps and the SYRK.
+int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch) {
   TcState *st = static_cast<TcState *>(c->tmap);
   if (!st) { balm_set_error("tensor path not initialised"); return BALM_ERR_INVALID; }
   const int ldq = c->ldg;
+  const int64_t rows = 3 * (v1 - v0);
   const int64_t rows_padded = (rows + KS - 1) / KS * KS;
+  CUDA_TRY(cudaMemsetAsync(st->colmax, 0, sizeof(unsigned long long) * ldq, c->stream));
+  int rc = launch_obs_colmax(c, poses, v0, v1);
+  if (rc != BALM_OK) return rc;
   tc_scale_kernel<<<(ldq + 255) / 256, 256, 0, c->stream>>>(st->colmax, st->sc, st->isc, ldq, st->S);
-  dim3 sgrid((unsigned)rows_padded, (ldq / 4 + 127) / 128);
-  tc_slice_kernel<<<sgrid, 128, 0, c->stream>>>(c->G, c->ldg, st->sc, c->Gq, ldq, rows, rows_padded,
-                                                (int64_t)st->rows_alloc * ldq, st->S);
-  CUDA_TRY(cudaEventRecord(c->ev[12], c->stream));  // end of the slice phase
+  rc = launch_obs_int8(c, poses, v0, v1, first_batch, st->sc, c->Gq, (int64_t)st->rows_alloc * ldq, st->S, rows_padded);
+  if (rc != BALM_OK) return rc;
+  CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
   TcArgs a{rows_padded, c->syrk_nb, c->syrk_tiles, c->syrk_splits, st->S, st->isc, c->syrk_part,
            first_batch ? 0 : 1, st->err, getenv("BALM_TC_COLLECTOR") ? 1 : 0};
   const int items = a.tiles * a.splits;
   const int grid = items < c->sm_count ? items : c->sm_count;
   const int smem = STAGES * STAGE_BYTES + 1024 + 256;
   syrk_tc_kernel<<<grid, TC_THREADS, smem, c->stream>>>(st->map, a);
-  c->launches += 3;
+  c->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return BALM_OK;
 }
