@@ -156,7 +156,7 @@ extern "C" int balm_create(balm_ctx **out, int n_poses, int device, int precisio
   TRY(dev_alloc(&c->scal, 16));
   TRY(dev_alloc(&c->flags, 4));
   TRY(dev_alloc(&c->accum, (size_t)BALM_ACC * c->Np));
-  c->res_blocks = c->sm_count * 16;
+  c->res_blocks = c->sm_count * 24;  // residual partials: one per warp of the stats kernel (3 CTAs x 8 warps per SM)
   TRY(dev_alloc(&c->res_part, (size_t)c->res_blocks));
   CUDA_TRY(cudaMallocHost((void **)&c->h_scal, 16 * sizeof(double)));
   CUDA_TRY(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int)));

@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int STATS_THREADS = 128;
+constexpr int STATS_THREADS = 256;
 
 struct StatsArgs {
   const double *obs;
@@ -26,6 +26,7 @@ struct StatsArgs {
   const double *fix;  // SoA [10][M] or null
   int64_t M;
   const double *poses;
+  int N;
   int64_t v0, v1;
   double *stats;      // [v1-v0][20] or null
   double *res_part;   // [gridDim.x]
@@ -35,8 +36,14 @@ struct StatsArgs {
 // so the serial eigen-solve of one voxel overlaps the loads of the others. Lanes stride over the voxel's
 // observations with two observations (20 independent 8-byte loads) in flight per lane.
 constexpr int STATS_WARPS = STATS_THREADS / 32;
-template <bool STORE>
-__global__ void __launch_bounds__(STATS_THREADS) voxel_stats_kernel(StatsArgs a) {
+template <bool STORE, bool SMEM_POSES>
+__global__ void __launch_bounds__(STATS_THREADS, 3) voxel_stats_kernel(StatsArgs a) {
+  extern __shared__ double s_poses[];  // [12 * N] pose table (R column-major, p): 96 B per pose, read per observation
+  if (SMEM_POSES) {
+    for (int e = threadIdx.x; e < 12 * a.N; e += STATS_THREADS) s_poses[e] = a.poses[e];
+    __syncthreads();
+  }
+  const double *ptab = SMEM_POSES ? s_poses : a.poses;
   const int lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * STATS_WARPS + (threadIdx.x >> 5);
   const int64_t nw = (int64_t)gridDim.x * STATS_WARPS;
@@ -57,12 +64,12 @@ __global__ void __launch_bounds__(STATS_THREADS) voxel_stats_kernel(StatsArgs a)
       for (int c = 0; c < 10; c++) { oa[c] = __ldg(a.obs + c * a.Kp + sA); ob[c] = __ldg(a.obs + c * a.Kp + sB); }
       const int pa = __ldg(a.pose_idx + sA), pb = __ldg(a.pose_idx + sB);
       double r[9], p[3];
-      load_pose(a.poses + 12 * pa, r, p);
+      load_pose_any<SMEM_POSES>(ptab + 12 * pa, r, p);
       WC w = world_cluster(oa, r, p);
       acc[0] += w.p00; acc[1] += w.p01; acc[2] += w.p02; acc[3] += w.p11; acc[4] += w.p12;
       acc[5] += w.p22; acc[6] += w.v0;  acc[7] += w.v1;  acc[8] += w.v2;  acc[9] += w.n;
       if (hasB) {
-        load_pose(a.poses + 12 * pb, r, p);
+        load_pose_any<SMEM_POSES>(ptab + 12 * pb, r, p);
         w = world_cluster(ob, r, p);
         acc[0] += w.p00; acc[1] += w.p01; acc[2] += w.p02; acc[3] += w.p11; acc[4] += w.p12;
         acc[5] += w.p22; acc[6] += w.v0;  acc[7] += w.v1;  acc[8] += w.v2;  acc[9] += w.n;
@@ -348,10 +355,23 @@ int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1,
   const int64_t want = (nv + STATS_WARPS - 1) / STATS_WARPS;
   const int max_blocks = c->res_blocks / STATS_WARPS;
   int blocks = (int)(want < (int64_t)max_blocks ? want : max_blocks);
-  StatsArgs a{c->obs, c->Kp, c->pose_idx, c->row_ptr, c->coe, use_fix ? c->fix : nullptr, c->M, poses, v0, v1,
+  StatsArgs a{c->obs, c->Kp, c->pose_idx, c->row_ptr, c->coe, use_fix ? c->fix : nullptr, c->M, poses, c->N, v0, v1,
               store_stats ? c->stats : nullptr, c->res_part};
-  if (store_stats) voxel_stats_kernel<true><<<blocks, STATS_THREADS, 0, c->stream>>>(a);
-  else voxel_stats_kernel<false><<<blocks, STATS_THREADS, 0, c->stream>>>(a);
+  const int psmem = 12 * c->N * (int)sizeof(double);
+  const bool in_smem = psmem <= 64 * 1024;  // up to 682 poses; larger windows read the table through L1
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(voxel_stats_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(voxel_stats_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  if (in_smem) {
+    if (store_stats) voxel_stats_kernel<true, true><<<blocks, STATS_THREADS, psmem, c->stream>>>(a);
+    else voxel_stats_kernel<false, true><<<blocks, STATS_THREADS, psmem, c->stream>>>(a);
+  } else {
+    if (store_stats) voxel_stats_kernel<true, false><<<blocks, STATS_THREADS, 0, c->stream>>>(a);
+    else voxel_stats_kernel<false, false><<<blocks, STATS_THREADS, 0, c->stream>>>(a);
+  }
   residual_reduce_kernel<<<1, 32, 0, c->stream>>>(c->res_part, blocks * STATS_WARPS, residual_out_dev, 1);
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());

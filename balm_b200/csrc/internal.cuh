@@ -140,6 +140,19 @@ __device__ __forceinline__ void load_pose(const double *__restrict__ pose12, dou
   p[2] = __ldg(pose12 + 11);
 }
 
+template <bool PLAIN>
+__device__ __forceinline__ void load_pose_any(const double *pose12, double *r, double *p) {
+  if (PLAIN) {  // shared-memory table
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int rr = 0; rr < 3; rr++) r[rr * 3 + c] = pose12[c * 3 + rr];
+    p[0] = pose12[9]; p[1] = pose12[10]; p[2] = pose12[11];
+  } else {
+    load_pose(pose12, r, p);
+  }
+}
+
 #define BALM_JROT(app, aqq, apq, arp, arq, vp0, vp1, vp2, vq0, vq1, vq2)        \
   if (apq != 0.0) {                                                             \
     const double th = (aqq - app) / (2.0 * apq);                                \

@@ -39,84 +39,141 @@ __global__ void damp_copy_kernel(const double *H, double *A, double *dvec, int n
 //     it to the right-hand side: y_j = L11^-1 b_j (forward substitution fused into the factorisation).
 // (2) ldl_panel_kernel: W = A21 X^T (64x64x64 GEMM per 64-row tile), L21 = W d^-1, b_rows -= L21 y_j.
 // (3) ldl_update_kernel: A22 -= L21 W^T on 128x128 tiles of the lower triangle.
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// The 64x64 diagonal block is factored in four 16-column sub-panels. A sub-panel is factored by TWO warps (one
+// thread per row, its 16 panel entries in registers) with a 64-thread named barrier per column -- the serial chain
+// of the whole solve is n = 6N of these column steps, so each step is kept to: post column -> barrier -> reciprocal
+// -> <=15 FMAs. The rank-16 trailing update and the assembly of X = L11^-1 from 16x16 inverses use all 256 threads.
 __global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0, int nbw, double *Xcm, double *dinv_all,
                                                        double *sol, int *flags) {
-  __shared__ double colA[2][NB], rowX[2][NB], bvec[NB], ypart[NB];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // rows 4*tx.., cols 4*ty..
-  double a[4][4], x[4][4];
-#pragma unroll
-  for (int p = 0; p < 4; p++)
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int r = 4 * tx + p, c = 4 * ty + q;
-      double v = (r == c) ? 1.0 : 0.0;  // padding rows/cols of a short last panel act as identity
-      if (r < nbw && c < nbw && r >= c) v = A[(size_t)(j0 + c) * n + j0 + r];
-      a[p][q] = v;
-      x[p][q] = (r == c) ? 1.0 : 0.0;
-    }
+  extern __shared__ double dyn_smem[];
+  double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);                   // the block (lower) -> L, d
+  double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));  // L11^-1
+  double (*Wp)[17] = reinterpret_cast<double (*)[17]>(dyn_smem + 2 * NB * (NB + 1));     // current sub-panel times d
+  double (*col16)[16] = reinterpret_cast<double (*)[16]>(dyn_smem + 2 * NB * (NB + 1) + NB * 17);
+  double *bvec = dyn_smem + 2 * NB * (NB + 1) + NB * 17 + 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e & (NB - 1), c = e >> 6;
+    double v = (r == c) ? 1.0 : 0.0;  // rows/cols of a short last panel act as identity
+    if (r < nbw && c < nbw && r >= c) v = A[(size_t)(j0 + c) * n + j0 + r];
+    S[r][c] = v;
+    Xs[r][c] = 0.0;
+  }
   if (tid < NB) bvec[tid] = tid < nbw ? sol[j0 + tid] : 0.0;
+  __syncthreads();
   bool bad = false;
 #pragma unroll 1
-  for (int jq = 0; jq < NB / 4; jq++) {
+  for (int cb = 0; cb < NB; cb += 16) {
+    if (tid < NB) {  // ---- sub-panel factorisation: rows r >= cb, columns cb .. cb+15 ----
+      const int r = tid;
+      double a[16];
 #pragma unroll
-    for (int jr = 0; jr < 4; jr++) {  // compile-time register indices
-      const int j = 4 * jq + jr, buf = jr & 1;
-      if (ty == jq) {
+      for (int k = 0; k < 16; k++) a[k] = S[r][cb + k];
 #pragma unroll
-        for (int p = 0; p < 4; p++) colA[buf][4 * tx + p] = a[p][jr];
+      for (int j = 0; j < 16; j++) {
+        const int jc = cb + j;
+        if (r >= cb && r < cb + 16) col16[j & 1][r - cb] = a[j];  // unscaled column j at the panel's own rows
+        bar_sync_named(1, NB);
+        const double d = col16[j & 1][j];
+        if (!(fabs(d) > 1e-290 && fabs(d) < 1e300)) bad = true;
+        const double dinv = __drcp_rn(d);
+        if (r > jc) {
+          const double l = a[j] * dinv;
+#pragma unroll
+          for (int k = j + 1; k < 16; k++) a[k] -= l * col16[j & 1][k];
+          a[j] = l;
+        }
       }
-      if (tx == jq) {
+      if (r >= cb) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) rowX[buf][4 * ty + q] = x[jr][q];
-      }
-      __syncthreads();
-      const double d = colA[buf][j];
-      if (!(fabs(d) > 1e-290 && fabs(d) < 1e300)) bad = true;
-      const double dinv = __drcp_rn(d);  // correctly rounded reciprocal, far shorter than the IEEE division path
-      double lr[4], cc[4], xr[4];
-#pragma unroll
-      for (int p = 0; p < 4; p++) lr[p] = colA[buf][4 * tx + p] * dinv;  // L[r][j]
-#pragma unroll
-      for (int q = 0; q < 4; q++) { cc[q] = colA[buf][4 * ty + q]; xr[q] = rowX[buf][4 * ty + q]; }
-#pragma unroll
-      for (int p = 0; p < 4; p++) {
-        const int r = 4 * tx + p;
-        if (r > j) {
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int c = 4 * ty + q;
-            if (c > j && r >= c) a[p][q] -= lr[p] * cc[q];
-            x[p][q] -= lr[p] * xr[q];
-          }
-          if (ty == jq) a[p][jr] = lr[p];
+        for (int k = 0; k < 16; k++) {
+          if (r >= cb + k) S[r][cb + k] = a[k];        // L (r > cb+k) and d (r == cb+k)
         }
       }
     }
+    __syncthreads();
+    if (tid < NB) {  // W = L_panel * d for the trailing update
+      const int r = tid;
+#pragma unroll
+      for (int k = 0; k < 16; k++) Wp[r][k] = (r > cb + k) ? S[r][cb + k] * S[cb + k][cb + k] : 0.0;
+    }
+    __syncthreads();
+    const int t0 = cb + 16, tsz = NB - t0;  // trailing block
+    for (int e = tid; e < tsz * tsz; e += 256) {
+      const int r = t0 + e / tsz, c = t0 + e % tsz;
+      if (r >= c) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) s += Wp[r][k] * S[c][cb + k];
+        S[r][c] -= s;
+      }
+    }
+    __syncthreads();
   }
   if (bad && tid == 0) atomicOr(&flags[0], 1);
-  // write back L11 (strict lower) and d (diagonal); X column-major; d^-1
+
+  // ---- X = L11^-1: 16x16 diagonal-block inverses (one warp each, shuffles only) ----
+  if (warp < 4) {
+    const int cb = 16 * warp, i = lane & 15;
+    double xr[16];
 #pragma unroll
-  for (int p = 0; p < 4; p++)
+    for (int k = 0; k < 16; k++) xr[k] = (k == i) ? 1.0 : 0.0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int r = 4 * tx + p, c = 4 * ty + q;
-      if (r < nbw && c < nbw && r >= c) A[(size_t)(j0 + c) * n + j0 + r] = a[p][q];
-      Xcm[c * NB + r] = x[p][q];
-      if (r == c && r < nbw) dinv_all[j0 + r] = 1.0 / a[p][q];
+    for (int j = 0; j < 15; j++) {
+      const double l = (i > j) ? S[cb + i][cb + j] : 0.0;
+#pragma unroll
+      for (int k = 0; k <= j; k++) {  // row j of the inverse is final and has entries k <= j only
+        const double xj = __shfl_sync(0xffffffffu, xr[k], j, 16);
+        xr[k] -= l * xj;
+      }
     }
-  // y_j = X b_j : partial over this thread's 4 columns, reduced over ty through shared memory
-  __syncthreads();
-  if (tid < NB) ypart[tid] = 0.0;
-  __syncthreads();
+    if (lane < 16) {
 #pragma unroll
-  for (int p = 0; p < 4; p++) {
-    double s = 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) s += x[p][q] * bvec[4 * ty + q];
-    atomicAdd(&ypart[4 * tx + p], s);
+      for (int k = 0; k < 16; k++) Xs[cb + i][cb + k] = xr[k];
+    }
   }
   __syncthreads();
-  if (tid < nbw) sol[j0 + tid] = ypart[tid];
+  // ---- off-diagonal blocks by block rows: X_bc = -X_bb * sum_{m=c}^{b-1} L_bm X_mc ----
+#pragma unroll 1
+  for (int b = 1; b < 4; b++) {
+    const int rb = 16 * b;
+    for (int e = tid; e < 16 * rb; e += 256) {  // T[i][c] for i in block row b, c < rb
+      const int i = e / rb, c = e % rb;
+      double sacc = 0.0;
+      for (int m = c & ~15; m < rb; m++) sacc += S[rb + i][m] * Xs[m][c];  // Xs[m][c] = 0 for m < c
+      Xs[rb + i][c] = sacc;  // T parked in the (still zero) X_bc positions
+    }
+    __syncthreads();
+    for (int e = tid; e < 16 * rb; e += 256) {
+      const int i = e / rb, c = e % rb;
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; k++) sacc += Xs[rb + i][rb + k] * Xs[rb + k][c];  // X_bb (lower) times T
+      S[c][rb + i] = -sacc;  // T is still being read by other threads: stage the result in the free strict upper triangle of S
+    }
+    __syncthreads();
+    for (int e = tid; e < 16 * rb; e += 256) {
+      const int i = e / rb, c = e % rb;
+      Xs[rb + i][c] = S[c][rb + i];
+    }
+    __syncthreads();
+  }
+  // ---- write back L11 / d, X (column-major), 1/d, and y_j = X b_j ----
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e & (NB - 1), c = e >> 6;
+    if (r < nbw && c < nbw && r >= c) A[(size_t)(j0 + c) * n + j0 + r] = S[r][c];
+    Xcm[c * NB + r] = (r >= c) ? Xs[r][c] : 0.0;
+  }
+  if (tid < nbw) dinv_all[j0 + tid] = 1.0 / S[tid][tid];
+  if (tid < NB) {
+    double sacc = 0.0;
+    for (int c = 0; c <= tid; c++) sacc += Xs[tid][c] * bvec[c];
+    if (tid < nbw) sol[j0 + tid] = sacc;
+  }
 }
 
 __global__ void __launch_bounds__(256) ldl_panel_kernel(double *A, double *W, int n, int j0, int nbw, const double *Xcm,
@@ -188,60 +245,86 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 
-constexpr int UT = 128;  // update tile
-constexpr int UK = 32;   // k chunk
+constexpr int UT = 128;   // update tile
+constexpr int UKB = 16;   // k rows per pipeline stage
+constexpr int ULDS = UT + 4;  // padded smem row (doubles): conflict-free DMMA fragment loads (see syrk_f64.cu)
+constexpr int USTAGE = 2 * UKB * ULDS;
+
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Trailing update A22 -= L21 * W^T on 128x128 tiles of the lower triangle with fp64 tensor-core MMAs
+// (mma.sync.m8n8k4.f64, 8 warps x (64x32) warp tiles, cp.async double-buffered k slabs of 16).
 __global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double *W, int n, int j0, int nbw) {
-  extern __shared__ double dyn_smem[];
-  double (*sL)[UT + 4] = reinterpret_cast<double (*)[UT + 4]>(dyn_smem);                  // [k][row]
-  double (*sW)[UT + 4] = reinterpret_cast<double (*)[UT + 4]>(dyn_smem + UK * (UT + 4));  // [k][col]
+  extern __shared__ __align__(16) double dyn_smem[];
   const int base = j0 + nbw;
   int t = blockIdx.x, tr = 0;
   while (t >= tr + 1) { t -= tr + 1; tr++; }
   const int tc = t;  // tc <= tr
   const int r0 = base + tr * UT, c0 = base + tc * UT;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  double acc[8][8] = {};
-  for (int k0 = 0; k0 < nbw; k0 += UK) {
-    __syncthreads();
-    // 16-byte cp.async pieces (n, r0, c0 are even, so a pair is entirely inside or outside the matrix)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3, fr = lane >> 2, fk = lane & 3;
+  double acc[8][4][2];
 #pragma unroll
-    for (int it = 0; it < (UK * UT / 2) / 256; it++) {
-      const int e = tid + it * 256, rr = (e & (UT / 2 - 1)) * 2, k = e >> 6;
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int nsteps = (nbw + UKB - 1) / UKB;
+  auto load_stage = [&](int stage, int step) {
+    double *sL = dyn_smem + stage * USTAGE;
+    double *sW = sL + UKB * ULDS;
+    const int k0 = step * UKB;
+    // 16-byte pieces; n, r0, c0 are even so a pair is entirely inside or outside the matrix
+    for (int e = tid; e < UKB * (UT / 2); e += 256) {
+      const int k = e >> 6, rr = (e & 63) * 2;
       const bool kv = k0 + k < nbw;
-      if (kv && r0 + rr < n) cp_async16(&sL[k][rr], A + (size_t)(j0 + k0 + k) * n + r0 + rr);
-      else *reinterpret_cast<double2 *>(&sL[k][rr]) = make_double2(0.0, 0.0);
-      if (kv && c0 + rr < n) cp_async16(&sW[k][rr], W + (size_t)(k0 + k) * n + c0 + rr);
-      else *reinterpret_cast<double2 *>(&sW[k][rr]) = make_double2(0.0, 0.0);
+      if (kv && r0 + rr < n) cp_async16(sL + k * ULDS + rr, A + (size_t)(j0 + k0 + k) * n + r0 + rr);
+      else *reinterpret_cast<double2 *>(sL + k * ULDS + rr) = make_double2(0.0, 0.0);
+      if (kv && c0 + rr < n) cp_async16(sW + k * ULDS + rr, W + (size_t)(k0 + k) * n + c0 + rr);
+      else *reinterpret_cast<double2 *>(sW + k * ULDS + rr) = make_double2(0.0, 0.0);
     }
-    asm volatile("cp.async.commit_group;\n" ::);
-    asm volatile("cp.async.wait_group 0;\n" ::);
+  };
+  load_stage(0, 0);
+  asm volatile("cp.async.commit_group;\n" ::);
+  for (int step = 0; step < nsteps; step++) {
+    if (step + 1 < nsteps) {
+      load_stage((step + 1) & 1, step + 1);
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
     __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < UK; k++) {
-      double lv[8], wv[8];
+    const double *sL = dyn_smem + (step & 1) * USTAGE;
+    const double *sW = sL + UKB * ULDS;
 #pragma unroll
-      for (int p = 0; p < 4; p++) {
-        lv[p] = sL[k][4 * tx + p];
-        lv[4 + p] = sL[k][64 + 4 * tx + p];
-        wv[p] = sW[k][4 * ty + p];
-        wv[4 + p] = sW[k][64 + 4 * ty + p];
+    for (int kk = 0; kk < UKB; kk += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; i++) af[i] = sL[(kk + fk) * ULDS + wm * 64 + i * 8 + fr];
+#pragma unroll
+      for (int j = 0; j < 4; j++) bf[j] = sW[(kk + fk) * ULDS + wn * 32 + j * 8 + fr];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int row = r0 + wm * 64 + i * 8 + fr;
+      const int col = c0 + wn * 32 + j * 8 + 2 * fk;
+      if (row < n) {
+        if (col < n && row >= col) A[(size_t)col * n + row] -= acc[i][j][0];
+        if (col + 1 < n && row >= col + 1) A[(size_t)(col + 1) * n + row] -= acc[i][j][1];
       }
-#pragma unroll
-      for (int p = 0; p < 8; p++)
-#pragma unroll
-        for (int q = 0; q < 8; q++) acc[p][q] += lv[p] * wv[q];
     }
-  }
-#pragma unroll
-  for (int q = 0; q < 8; q++) {
-    const int col = c0 + (q < 4 ? 4 * ty + q : 64 + 4 * ty + q - 4);
-    if (col >= n) continue;
-#pragma unroll
-    for (int p = 0; p < 8; p++) {
-      const int row = r0 + (p < 4 ? 4 * tx + p : 64 + 4 * tx + p - 4);
-      if (row < n && row >= col) A[(size_t)col * n + row] -= acc[p][q];
-    }
-  }
 }
 
 // rhs = -g (start of the forward substitution, fused into the factorisation kernels)
@@ -355,6 +438,8 @@ __global__ void gauge_kernel(double *poses, const double *pose0_snapshot, int N,
 
 }  // namespace
 
+constexpr int DIAG_SMEM = (2 * NB * (NB + 1) + NB * 17 + 32 + NB) * (int)sizeof(double);
+
 static int enqueue_solve(balm_ctx *c) {
   const int n = c->n;
   cudaStream_t st = c->stream;
@@ -362,12 +447,12 @@ static int enqueue_solve(balm_ctx *c) {
   damp_copy_kernel<<<g1, 256, 0, st>>>(c->H, c->A, c->dvec, n, c->scal + 3);
   rhs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->g, c->sol, n);
   const int panel_smem = 2 * NB * (NB + 4) * (int)sizeof(double);
-  const int update_smem = 2 * UK * (UT + 4) * (int)sizeof(double);
+  const int update_smem = 2 * USTAGE * (int)sizeof(double);
   int launches = 2;
   for (int j0 = 0, pi = 0; j0 < n; j0 += NB, pi++) {
     const int nbw = (n - j0 < NB) ? n - j0 : NB;
     double *X = c->Xinv + (size_t)pi * NB * NB;
-    ldl_diag_kernel<<<1, 256, 0, st>>>(c->A, n, j0, nbw, X, c->dinv, c->sol, c->flags);
+    ldl_diag_kernel<<<1, 256, DIAG_SMEM, st>>>(c->A, n, j0, nbw, X, c->dinv, c->sol, c->flags);
     launches++;
     const int m = n - j0 - nbw;
     if (m > 0) {
@@ -400,7 +485,8 @@ int launch_ldlt_solve(balm_ctx *c, double u) {
     CUDA_TRY(cudaFuncSetAttribute(ldl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   2 * NB * (NB + 4) * (int)sizeof(double)));
     CUDA_TRY(cudaFuncSetAttribute(ldl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  2 * UK * (UT + 4) * (int)sizeof(double)));
+                                  2 * USTAGE * (int)sizeof(double)));
+    CUDA_TRY(cudaFuncSetAttribute(ldl_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     attr_set2 = true;
   }
   if (!c->Xinv) {

@@ -10,13 +10,13 @@
 // (S = 4) and the dropped digit pairs s+t >= S (same order); integer accumulation is associative, so the
 // result does not depend on tile order, k-splits or the number of GPUs.
 //
-// Kernel anatomy (one CTA per SM, persistent over (tile, k-split) items, 192 threads):
+// Kernel anatomy (one CTA per SM, persistent over (tile, k-split) items, 320 threads):
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor.3d of the S int8 planes of the A (rows bi) and B (rows bj)
 //              128-column blocks, 128B-swizzled, into a 3-stage shared-memory ring (mbarrier full/empty)
 //   warp 1   : MMA issuer    -- one elected lane issues tcgen05.mma.cta_group::1.kind::i8, M=128 N=128 K=32,
 //              both operands MN-major (pose index contiguous), S(S+1)/2 = 10 digit-pair products per K step
 //              into S accumulators (S*128 = 512 TMEM columns); tcgen05.commit releases the smem stage
-//   warps 2-5: epilogue      -- tcgen05.ld 32x32b of the S accumulators, fp64 Horner combine, column scales,
+//   warps 2-9: epilogue      -- tcgen05.ld 32x32b of the S accumulators, fp64 Horner combine, column scales,
 //              fp64 partial tile to global (same partial layout as the fp64 path -> same assemble kernel)
 #include <cuda.h>
 #include "internal.cuh"
@@ -30,7 +30,7 @@ constexpr int UMMA_K = 32;            // int8
 constexpr int STAGES = 3;
 constexpr int PLANE_TILE_BYTES = KS * TILE;             // 8192: one plane, one operand, one stage
 constexpr int STAGE_BYTES = 2 * SMAX * PLANE_TILE_BYTES;  // 65536
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int MAX_ROWS_PER_ITEM = 32768 - KS;           // S * rows * 2^14 < 2^31
 
 // ---------------- PTX wrappers ----------------
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);
+    mbar_init(tmem_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;                // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;         // which 64-column half of the tile this warp drains
     const int row = quad * 32 + lane;         // tile row held by this thread
     uint32_t n_done = 0;
     const double inv256 = 1.0 / 256.0;
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
       const double isc_row = __ldg(a.isc + bi * TILE + row);
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < TILE; c0 += 16) {
+      for (int c0 = half * (TILE / 2); c0 < (half + 1) * (TILE / 2); c0 += 16) {
         double val[16];
         if (empty_item) {
 #pragma unroll

@@ -251,3 +251,56 @@ def test_tensor_path_matches_fp64_path_c2():
     assert [t["accepted"] for t in tr0] == [t["accepted"] for t in tr1]
     for a, b in zip(per0, per1):
         assert max(_pose_err(a, b)) <= 1e-6
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("n_poses,n_planes,drop", [
+    (3, 2, 0.0),       # two voxels only
+    (130, 40, 0.0),    # N > 128: several pose tiles, n = 780 -> 7 column blocks with padding
+    (700, 12, 0.0),    # pose table larger than the 64 KB shared-memory staging of the stats kernel
+    (65, 33, 0.6),     # heavily ragged
+])
+def test_evaluate_edge_shapes(n_poses, n_planes, drop, prec):
+    sc = scenes.make_scene(n_poses=n_poses, n_planes=n_planes, seed=41, drop=drop, pts_size=8)
+    c, o = _ctx(sc, prec), _oracle(sc)
+    _check_eval(c, o, sc["poses_init"], tolH=TOLH[prec])
+    r = c.residual(sc["poses_init"])
+    assert abs(r - o.residual(sc["poses_init"])) <= 1e-12 * abs(r)
+
+
+def test_tensor_digit_planes_option(monkeypatch):
+    """BALM_TC_SLICES=3 (22-bit fixed point) still meets the pose contract; 4 planes (default) is tighter."""
+    sc = scenes.make_scene(n_poses=24, n_planes=300, seed=42)
+    o = _oracle(sc)
+    Ho, go, ro = o.evaluate(sc["poses_init"])
+    errs = {}
+    for S in (3, 4):
+        monkeypatch.setenv("BALM_TC_SLICES", str(S))
+        c = _ctx(sc, 1)
+        H, g, r = c.evaluate(sc["poses_init"])
+        errs[S] = np.abs(H - Ho).max() / np.abs(Ho).max()
+    assert errs[4] <= 1e-8 and errs[3] <= 5e-6 and errs[4] < errs[3]
+
+
+def test_evaluate_is_independent_of_history():
+    """The tensor path derives its column scales from the current poses only (two sweeps), so the same inputs give
+    the same bits whatever was evaluated before."""
+    sc = scenes.make_scene(n_poses=16, n_planes=120, seed=43)
+    c = _ctx(sc, 1)
+    H1, g1, r1 = c.evaluate(sc["poses_init"])
+    c.evaluate(sc["poses_gt"])
+    H2, g2, r2 = c.evaluate(sc["poses_init"])
+    assert np.array_equal(H1, H2) and np.array_equal(g1, g2) and r1 == r2
+
+
+def test_two_gpu_shards_match_single_gpu():
+    """Voxel shards on two GPUs + NCCL all-reduce of [H|g|r] == one GPU with all voxels (needs >= 2 GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "scripts", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
