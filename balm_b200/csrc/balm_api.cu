@@ -183,29 +183,67 @@ extern "C" int balm_destroy(balm_ctx *c) {
 }
 
 // ---------------- problem registration ----------------
-static int finish_registration(balm_ctx *c, const std::vector<int64_t> &row_ptr, const std::vector<int32_t> &pidx) {
+// One thread per voxel: checks the CSR invariants (pose_idx ascending, in range), finds the widest voxel and whether
+// every voxel is observed by every pose; one thread per observation builds the per-pose voxel histogram
+// (the ">= 20 planes per pose" precheck of bavoxel.hpp:1071-1085). Replaces a host loop over all K observations.
+__global__ void csr_check_kernel(const long long *row_ptr, const int *pose_idx, int64_t M, int N, int *out /*[3]*/) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= M) return;
+  const long long s0 = row_ptr[v], s1 = row_ptr[v + 1];
+  const int k = (int)(s1 - s0);
+  bool bad = (s1 < s0);
+  int prev = -1;
+  for (long long s = s0; s < s1; s++) {
+    const int p = pose_idx[s];
+    if (p <= prev || p >= N) bad = true;
+    prev = p;
+  }
+  if (bad) atomicOr(&out[0], 1);
+  if (k != N) atomicOr(&out[1], 1);  // not dense
+  atomicMax(&out[2], k);
+}
+__global__ void pose_hist_kernel(const int *pose_idx, int64_t K, int N, int *planes) {
+  extern __shared__ int hist[];
+  for (int e = threadIdx.x; e < N; e += blockDim.x) hist[e] = 0;
+  __syncthreads();
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < K; s += (int64_t)gridDim.x * blockDim.x) {
+    const int p = pose_idx[s];
+    if (p >= 0 && p < N) atomicAdd(&hist[p], 1);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < N; e += blockDim.x)
+    if (hist[e]) atomicAdd(&planes[e], hist[e]);
+}
+static int finish_registration(balm_ctx *c) {
   const int N = c->N;
   const int64_t M = c->M;
-  std::vector<int> planes(N, 0);
-  bool dense = true;
-  int max_k = 0;
-  for (int64_t v = 0; v < M; v++) {
-    const int64_t k = row_ptr[v + 1] - row_ptr[v];
-    if (k > max_k) max_k = (int)k;
-    if (k != N) dense = false;
-    for (int64_t s = row_ptr[v]; s < row_ptr[v + 1]; s++) {
-      const int p = pidx[s];
-      if (p < 0 || p >= N || (s > row_ptr[v] && p <= pidx[s - 1])) {
-        balm_set_error("balm_set_voxels: pose_idx must be ascending and in [0,N) inside each voxel");
-        return BALM_ERR_INVALID;
-      }
-      planes[p]++;
-    }
+  int *d_out = nullptr, *d_planes = nullptr;
+  TRY(dev_alloc(&d_out, 4));
+  TRY(dev_alloc(&d_planes, (size_t)N));
+  CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(int) * 4, c->stream));
+  CUDA_TRY(cudaMemsetAsync(d_planes, 0, sizeof(int) * N, c->stream));
+  csr_check_kernel<<<(unsigned)((M + 127) / 128), 128, 0, c->stream>>>(c->row_ptr, c->pose_idx, M, N, d_out);
+  pose_hist_kernel<<<c->sm_count * 4, 256, sizeof(int) * N, c->stream>>>(c->pose_idx, c->K, N, d_planes);
+  c->launches += 2;
+  int h_out[4];
+  std::vector<int> planes(N);
+  CUDA_TRY(cudaMemcpyAsync(h_out, d_out, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(planes.data(), d_planes, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  cudaFree(d_out); cudaFree(d_planes);
+  if (h_out[0]) {
+    balm_set_error("balm_set_voxels: pose_idx must be ascending and in [0,N) inside each voxel");
+    return BALM_ERR_INVALID;
   }
+  const bool dense = h_out[1] == 0;
   c->dense = dense;
-  c->max_k = max_k;
+  c->max_k = h_out[2];
   c->min_planes = *std::min_element(planes.begin(), planes.end());
-  if (!dense) {  // pose-major lists for the observation pass
+  if (!dense) {  // pose-major lists for the observation pass (sparse problems are small: built on the host)
+    std::vector<int64_t> row_ptr(M + 1);
+    std::vector<int32_t> pidx(c->K);
+    CUDA_TRY(cudaMemcpy(row_ptr.data(), c->row_ptr, sizeof(int64_t) * (M + 1), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(pidx.data(), c->pose_idx, sizeof(int32_t) * c->K, cudaMemcpyDeviceToHost));
     std::vector<int> ptr(N + 1, 0), cobs(c->K), cvox(c->K);
     for (int i = 0; i < N; i++) ptr[i + 1] = ptr[i] + planes[i];
     std::vector<int> cur(ptr.begin(), ptr.end() - 1);
@@ -277,9 +315,7 @@ extern "C" int balm_set_voxels(balm_ctx *c, int64_t M, const int64_t *row_ptr, c
   CUDA_TRY(cudaMemcpyAsync(c->coe, coe, sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
   TRY(upload_aos(c, obs10, false, c->obs, K, c->Kp));
   if (fix10) TRY(upload_aos(c, fix10, false, c->fix, M, M));
-  std::vector<int64_t> rp(row_ptr, row_ptr + M + 1);
-  std::vector<int32_t> pi(pose_idx, pose_idx + K);
-  return finish_registration(c, rp, pi);
+  return finish_registration(c);
 }
 
 extern "C" int balm_set_voxels_dev(balm_ctx *c, int64_t M, const int64_t *row_ptr_dev, const int32_t *pose_idx_dev,
@@ -296,11 +332,7 @@ extern "C" int balm_set_voxels_dev(balm_ctx *c, int64_t M, const int64_t *row_pt
   CUDA_TRY(cudaMemcpyAsync(c->coe, coe_dev, sizeof(double) * M, cudaMemcpyDeviceToDevice, c->stream));
   TRY(upload_aos(c, obs10_dev, true, c->obs, K, c->Kp));
   if (fix10_dev) TRY(upload_aos(c, fix10_dev, true, c->fix, M, M));
-  std::vector<int64_t> rp(M + 1);
-  std::vector<int32_t> pi(K);
-  CUDA_TRY(cudaMemcpy(rp.data(), c->row_ptr, sizeof(int64_t) * (M + 1), cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(pi.data(), c->pose_idx, sizeof(int32_t) * K, cudaMemcpyDeviceToHost));
-  return finish_registration(c, rp, pi);
+  return finish_registration(c);
 }
 
 extern "C" int64_t balm_num_obs(balm_ctx *c) { return c ? c->K : 0; }
