@@ -56,14 +56,24 @@ __global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0,
   double (*col16)[16] = reinterpret_cast<double (*)[16]>(dyn_smem + 2 * NB * (NB + 1) + NB * 17);
   double *bvec = dyn_smem + 2 * NB * (NB + 1) + NB * 17 + 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e & (NB - 1), c = e >> 6;
-    double v = (r == c) ? 1.0 : 0.0;  // rows/cols of a short last panel act as identity
-    if (r < nbw && c < nbw && r >= c) v = A[(size_t)(j0 + c) * n + j0 + r];
-    S[r][c] = v;
-    Xs[r][c] = 0.0;
+  {
+    double ld[16];  // all 16 global loads of this thread in flight together (the kernel is pure latency)
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+      const int e = tid + it * 256, r = e & (NB - 1), c = e >> 6;
+      double v = (r == c) ? 1.0 : 0.0;  // rows/cols of a short last panel act as identity
+      if (r < nbw && c < nbw && r >= c) v = A[(size_t)(j0 + c) * n + j0 + r];
+      ld[it] = v;
+    }
+    const double bv = (tid < nbw) ? sol[j0 + tid] : 0.0;
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+      const int e = tid + it * 256, r = e & (NB - 1), c = e >> 6;
+      S[r][c] = ld[it];
+      Xs[r][c] = 0.0;
+    }
+    if (tid < NB) bvec[tid] = bv;
   }
-  if (tid < NB) bvec[tid] = tid < nbw ? sol[j0 + tid] : 0.0;
   __syncthreads();
   bool bad = false;
 #pragma unroll 1
@@ -102,15 +112,18 @@ __global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0,
       for (int k = 0; k < 16; k++) Wp[r][k] = (r > cb + k) ? S[r][cb + k] * S[cb + k][cb + k] : 0.0;
     }
     __syncthreads();
-    const int t0 = cb + 16, tsz = NB - t0;  // trailing block
-    for (int e = tid; e < tsz * tsz; e += 256) {
-      const int r = t0 + e / tsz, c = t0 + e % tsz;
-      if (r >= c) {
-        double s = 0.0;
+    {  // trailing block in 16x16 sub-blocks: thread (ri, ci) owns one element of each lower sub-block
+      const int ri = tid >> 4, ci = tid & 15;
+      for (int rb2 = cb + 16; rb2 < NB; rb2 += 16)
+        for (int cb2 = cb + 16; cb2 <= rb2; cb2 += 16) {
+          const int r = rb2 + ri, c = cb2 + ci;
+          if (r >= c) {
+            double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) s += Wp[r][k] * S[c][cb + k];
-        S[r][c] -= s;
-      }
+            for (int k = 0; k < 16; k++) s += Wp[r][k] * S[c][cb + k];
+            S[r][c] -= s;
+          }
+        }
     }
     __syncthreads();
   }
@@ -140,29 +153,34 @@ __global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0,
   // ---- off-diagonal blocks by block rows: X_bc = -X_bb * sum_{m=c}^{b-1} L_bm X_mc ----
 #pragma unroll 1
   for (int b = 1; b < 4; b++) {
-    const int rb = 16 * b;
-    for (int e = tid; e < 16 * rb; e += 256) {  // T[i][c] for i in block row b, c < rb
-      const int i = e / rb, c = e % rb;
+    const int rb = 16 * b, ri = tid >> 4, ci = tid & 15;
+    for (int cq = 0; cq < b; cq++) {  // T_bc = sum_{m in blocks c..b-1} L_bm X_mc, parked in the X_bc positions
+      const int c = 16 * cq + ci;
       double sacc = 0.0;
-      for (int m = c & ~15; m < rb; m++) sacc += S[rb + i][m] * Xs[m][c];  // Xs[m][c] = 0 for m < c
-      Xs[rb + i][c] = sacc;  // T parked in the (still zero) X_bc positions
+      for (int m = 16 * cq; m < rb; m++) sacc += S[rb + ri][m] * Xs[m][c];
+      Xs[rb + ri][c] = sacc;
     }
     __syncthreads();
-    for (int e = tid; e < 16 * rb; e += 256) {
-      const int i = e / rb, c = e % rb;
-      double sacc = 0.0;
+    double xn[3];
 #pragma unroll
-      for (int k = 0; k < 16; k++) sacc += Xs[rb + i][rb + k] * Xs[rb + k][c];  // X_bb (lower) times T
-      S[c][rb + i] = -sacc;  // T is still being read by other threads: stage the result in the free strict upper triangle of S
+    for (int cq = 0; cq < 3; cq++) {
+      xn[cq] = 0.0;
+      if (cq < b) {
+        const int c = 16 * cq + ci;
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) sacc += Xs[rb + ri][rb + k] * Xs[rb + k][c];  // X_bb (lower) times T
+        xn[cq] = -sacc;
+      }
     }
-    __syncthreads();
-    for (int e = tid; e < 16 * rb; e += 256) {
-      const int i = e / rb, c = e % rb;
-      Xs[rb + i][c] = S[c][rb + i];
-    }
+    __syncthreads();  // every thread has read the T values it needs
+#pragma unroll
+    for (int cq = 0; cq < 3; cq++)
+      if (cq < b) Xs[rb + ri][16 * cq + ci] = xn[cq];
     __syncthreads();
   }
   // ---- write back L11 / d, X (column-major), 1/d, and y_j = X b_j ----
+#pragma unroll 4
   for (int e = tid; e < NB * NB; e += 256) {
     const int r = e & (NB - 1), c = e >> 6;
     if (r < nbw && c < nbw && r >= c) A[(size_t)(j0 + c) * n + j0 + r] = S[r][c];
@@ -246,9 +264,9 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 
 constexpr int UT = 128;   // update tile
-constexpr int UKB = 16;   // k rows per pipeline stage
+constexpr int UKB = 64;   // k rows per stage: the whole panel width in one shot (one global round trip)
 constexpr int ULDS = UT + 4;  // padded smem row (doubles): conflict-free DMMA fragment loads (see syrk_f64.cu)
-constexpr int USTAGE = 2 * UKB * ULDS;
+constexpr int USTAGE = 2 * UKB * ULDS;  // 135 KB: one CTA per SM
 
 __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -278,6 +296,7 @@ __global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double
     double *sW = sL + UKB * ULDS;
     const int k0 = step * UKB;
     // 16-byte pieces; n, r0, c0 are even so a pair is entirely inside or outside the matrix
+#pragma unroll 4
     for (int e = tid; e < UKB * (UT / 2); e += 256) {
       const int k = e >> 6, rr = (e & 63) * 2;
       const bool kv = k0 + k < nbw;
@@ -314,17 +333,25 @@ __global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double
     }
     __syncthreads();
   }
+  // read-modify-write of the C tile: all loads of a row group are issued before the first store, otherwise every
+  // "-=" serialises a full L2 round trip (64 of them per thread)
 #pragma unroll
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < 8; i++) {
+    const int row = r0 + wm * 64 + i * 8 + fr;
+    double cv[4][2];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const int row = r0 + wm * 64 + i * 8 + fr;
       const int col = c0 + wn * 32 + j * 8 + 2 * fk;
-      if (row < n) {
-        if (col < n && row >= col) A[(size_t)col * n + row] -= acc[i][j][0];
-        if (col + 1 < n && row >= col + 1) A[(size_t)(col + 1) * n + row] -= acc[i][j][1];
-      }
+      cv[j][0] = (row < n && col < n && row >= col) ? A[(size_t)col * n + row] : 0.0;
+      cv[j][1] = (row < n && col + 1 < n && row >= col + 1) ? A[(size_t)(col + 1) * n + row] : 0.0;
     }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int col = c0 + wn * 32 + j * 8 + 2 * fk;
+      if (row < n && col < n && row >= col) A[(size_t)col * n + row] = cv[j][0] - acc[i][j][0];
+      if (row < n && col + 1 < n && row >= col + 1) A[(size_t)(col + 1) * n + row] = cv[j][1] - acc[i][j][1];
+    }
+  }
 }
 
 // rhs = -g (start of the forward substitution, fused into the factorisation kernels)
@@ -447,7 +474,7 @@ static int enqueue_solve(balm_ctx *c) {
   damp_copy_kernel<<<g1, 256, 0, st>>>(c->H, c->A, c->dvec, n, c->scal + 3);
   rhs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->g, c->sol, n);
   const int panel_smem = 2 * NB * (NB + 4) * (int)sizeof(double);
-  const int update_smem = 2 * USTAGE * (int)sizeof(double);
+  const int update_smem = USTAGE * (int)sizeof(double);
   int launches = 2;
   for (int j0 = 0, pi = 0; j0 < n; j0 += NB, pi++) {
     const int nbw = (n - j0 < NB) ? n - j0 : NB;
@@ -485,7 +512,7 @@ int launch_ldlt_solve(balm_ctx *c, double u) {
     CUDA_TRY(cudaFuncSetAttribute(ldl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   2 * NB * (NB + 4) * (int)sizeof(double)));
     CUDA_TRY(cudaFuncSetAttribute(ldl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  2 * USTAGE * (int)sizeof(double)));
+                                  USTAGE * (int)sizeof(double)));
     CUDA_TRY(cudaFuncSetAttribute(ldl_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     attr_set2 = true;
   }
