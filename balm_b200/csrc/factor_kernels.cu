@@ -136,10 +136,11 @@ struct ObsArgs {
 // One lane = one pose; a warp covers 32 consecutive poses and walks a chunk of voxels, so the observation
 // loads of a dense scene (slot j == pose j) are coalesced and the 27 accumulators stay in registers.
 enum { OBS_FP64 = 0, OBS_MAXONLY = 1, OBS_INT8 = 2 };
-// MODE: OBS_FP64    writes fp64 G' (+ gradient / diagonal blocks)            [fp64 SYRK path]
-//       OBS_MAXONLY only the column maxima of G' (first sweep of the tensor path -> power-of-two column scales)
-//       OBS_INT8    writes the balanced base-256 digit planes of rint(G' * sc) directly (+ gradient / blocks),
-//                   so the tensor path never materialises G' in fp64
+// MODE: OBS_FP64    writes fp64 G' + gradient / diagonal blocks                          [fp64 SYRK path]
+//       OBS_MAXONLY first sweep of the tensor path: column maxima of G' (-> power-of-two column scales) and the
+//                   gradient / diagonal-block accumulators (kept here so that the second sweep is lean)
+//       OBS_INT8    second sweep: writes the balanced base-256 digit planes of rint(G' * sc) directly, so the
+//                   tensor path never materialises G' in fp64
 template <bool DENSE, int MODE>
 __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
           cmax[q] = fmax(cmax[q], fmax(fabs(gv[0][q]), fmax(fabs(gv[1][q]), fabs(gv[2][q]))));
       }
     }
-    if (MODE == OBS_MAXONLY) continue;
+    if (MODE == OBS_INT8) continue;  // gradient and diagonal blocks were accumulated by the first sweep
     // ---- gradient (bavoxel.hpp:381) ----
 #pragma unroll
     for (int q = 0; q < 6; q++) acc[q] += coe * gk[0][q];
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
     for (int q = 0; q < 6; q++)  // non-negative doubles order like their bit patterns
       atomicMax(a.colmax + 6 * i + q, (unsigned long long)__double_as_longlong(cmax[q]));
   }
-  if (MODE != OBS_MAXONLY && active) {
+  if (MODE != OBS_INT8 && active) {
     double *pp = a.part + (size_t)blockIdx.x * BALM_ACC * a.Np + i;
 #pragma unroll
     for (int q = 0; q < BALM_ACC; q++) pp[(size_t)q * a.Np] = acc[q];
@@ -424,22 +425,25 @@ int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bo
   return BALM_OK;
 }
 
-// tensor path, sweep 1: column maxima of G' only.
-int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1) {
+// tensor path, sweep 1: column maxima of G' + gradient / diagonal-block accumulators.
+int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch) {
   const int64_t nv = v1 - v0;
   if (nv <= 0) return BALM_OK;
   ObsArgs a;
   obs_fill(c, a, poses, v0, v1);
   dim3 grid;
-  obs_grid(c, a, nv, grid);
+  const int chunks = obs_grid(c, a, nv, grid);
   if (c->dense) obs_pass_kernel<true, OBS_MAXONLY><<<grid, 128, 0, c->stream>>>(a);
   else obs_pass_kernel<false, OBS_MAXONLY><<<grid, 128, 0, c->stream>>>(a);
-  c->launches += 1;
+  const int total = BALM_ACC * c->Np;
+  obs_reduce_kernel<<<(total + 255) / 256, 256, 0, c->stream>>>(c->obs_part, chunks, total, c->accum,
+                                                                first_batch ? 0 : 1);
+  c->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return BALM_OK;
 }
 
-// tensor path, sweep 2: int8 digit planes written directly (+ gradient / diagonal blocks).
+// tensor path, sweep 2: int8 digit planes written directly.
 int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch, const double *sc,
                     int8_t *Gq, int64_t plane_stride, int S, int64_t rows_padded) {
   const int64_t nv = v1 - v0;
@@ -457,12 +461,10 @@ int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bo
       CUDA_TRY(cudaMemsetAsync(Gq + (size_t)s * plane_stride + (size_t)3 * nv * c->ldg, 0,
                                (size_t)(rows_padded - 3 * nv) * c->ldg, c->stream));
   }
+  (void)chunks; (void)first_batch;
   if (c->dense) obs_pass_kernel<true, OBS_INT8><<<grid, 128, 0, c->stream>>>(a);
   else obs_pass_kernel<false, OBS_INT8><<<grid, 128, 0, c->stream>>>(a);
-  const int total = BALM_ACC * c->Np;
-  obs_reduce_kernel<<<(total + 255) / 256, 256, 0, c->stream>>>(c->obs_part, chunks, total, c->accum,
-                                                                first_batch ? 0 : 1);
-  c->launches += 2;
+  c->launches += 1;
   CUDA_TRY(cudaGetLastError());
   return BALM_OK;
 }

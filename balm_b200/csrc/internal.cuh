@@ -233,7 +233,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool store_stats, bool use_fix,
                        double *residual_out_dev);
 int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
-int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1);
+int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch, const double *sc,
                     int8_t *Gq, int64_t plane_stride, int S, int64_t rows_padded);
 int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);

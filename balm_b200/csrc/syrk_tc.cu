@@ -453,7 +453,7 @@ int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1
   const int64_t rows = 3 * (v1 - v0);
   const int64_t rows_padded = (rows + KS - 1) / KS * KS;
   CUDA_TRY(cudaMemsetAsync(st->colmax, 0, sizeof(unsigned long long) * ldq, c->stream));
-  int rc = launch_obs_colmax(c, poses, v0, v1);
+  int rc = launch_obs_colmax(c, poses, v0, v1, first_batch);
   if (rc != BALM_OK) return rc;
   tc_scale_kernel<<<(ldq + 255) / 256, 256, 0, c->stream>>>(st->colmax, st->sc, st->isc, ldq, st->S);
   rc = launch_obs_int8(c, poses, v0, v1, first_batch, st->sc, c->Gq, (int64_t)st->rows_alloc * ldq, st->S, rows_padded);
