@@ -280,9 +280,30 @@ def main():
         peak_tf, peak_note = pk["bf16_sus"], (f"bf16 dense sustained, {pk['src']}; the fp64 path runs on the DMMA "
                                               f"pipe whose nominal peak is 40 TFLOP/s (not in MEASURED_PEAKS.json)")
     ach_tf = flops / (syrk_ms * 1e-3) / 1e12
+    traffic = None  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_tensor_ncu_full_summary.json")))
+        for k_ in prof:
+            if args.precision == "tensor" and k_["kernel"].startswith("syrk_tc_kernel") and N == 500 and M == 100000:
+                def gb(x):
+                    v, u = x.split()
+                    return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+                traffic = gb(k_["dram__bytes_read.sum"]) + gb(k_["dram__bytes_write.sum"])
+    except Exception:
+        traffic = None
     roof = {"kernel": "syrk_f64_kernel" if args.precision == "fp64" else "syrk_tc_kernel", "bound": "tensor",
-            "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
-            "peak_note": peak_note, "algorithmic_flops_per_launch": flops, "ms_per_launch": syrk_ms}
+            "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
+            "peak_note": peak_note, "algorithmic_flops_per_launch": flops, "ms_per_launch": syrk_ms,
+            "traffic_note": "dram__bytes_read+write per launch from profiles/r1_tensor_ncu_full_summary.json; algorithmic "
+                            "bytes of this kernel = digit planes read once (3 x 3M x ldg B) + fp64 partial tiles written"}
+    if args.precision == "tensor":
+        planes = 3 if 3 * M >= 49152 else 4
+        pairs = planes * (planes + 1) // 2
+        int8_ops = 2.0 * pairs * 0.5 * (3072 // 128) * (3072 // 128 + 1) * 128 * 128 * 3 * M if N == 500 else None
+        roof["digit_planes"] = planes
+        if int8_ops:
+            roof["executed_int8_tops"] = int8_ops / (syrk_ms * 1e-3) / 1e12
+            roof["frac_of_int8_nominal_4500_tops"] = roof["executed_int8_tops"] / 4500.0
     if args.precision == "fp64":
         roof["frac_of_fp64_nominal_40tf"] = ach_tf / 40.0
     res_ms = tm["ms_residual"] / max(tm["n_residual"], 1)

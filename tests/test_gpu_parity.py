@@ -304,3 +304,21 @@ def test_two_gpu_shards_match_single_gpu():
                           "--master-addr", "127.0.0.1", "--master-port", "29533",
                           os.path.join(root, "scripts", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_c2_shape_per_iteration_parity_vs_oracle(prec):
+    """BASELINE config C2 shape (200 poses; voxel count scaled to what the CPU oracle finishes in seconds):
+    per-iteration pose parity with the oracle, 1e-6 rad / 1e-6 m, same accept/reject sequence."""
+    import balm_b200
+    N, M = 200, 600
+    c = balm_b200.Context(N, 0, prec)
+    gt, init = c.synth_virtual(M, seed=12)
+    row_ptr, pose_idx, obs10, coe = c.download_voxels()
+    o = orc.Oracle(N, row_ptr, pose_idx, obs10, coe)
+    poses, tr, per = c.damping_iter(init, max_iter=4, want_per_iter=True, gauge_mode=2)
+    st, poses_o, tr_o, per_o = o.damping_iter(init, max_iter=4, gauge_mode=2)
+    assert st == 0 and [t["accepted"] for t in tr] == [t["accepted"] for t in tr_o]
+    for it in range(len(tr)):
+        rot, tra = _pose_err(per[it], per_o[it])
+        assert rot <= 1e-6 and tra <= 1e-6, (it, rot, tra)
