@@ -113,12 +113,23 @@ static int alloc_workspaces(balm_ctx *c) {
   max_splits = (int)std::max<size_t>(1, std::min<size_t>(max_splits, part_budget / per_split));
   int best = 1;
   double best_eff = 0;
-  for (int s = 1; s <= max_splits; s++) {
+  // every split costs one fp64 partial tile per output tile (written by the SYRK epilogue, read by the assembly):
+  // the tensor path (6 ms SYRK) takes the SMALLEST split count that keeps the last wave >= 95 % full and respects
+  // the int32 exactness bound (<= 32704 contraction rows per item); the fp64 path (97 ms SYRK) maximises balance.
+  const int min_splits = c->prec == BALM_PREC_TENSOR ? (int)((rows + 32703) / 32704) : 1;
+  for (int s = std::min(min_splits, max_splits); s <= max_splits; s++) {
     const int items = c->syrk_tiles * s;
     const int waves = (items + c->sm_count - 1) / c->sm_count;
     const double eff = (double)items / ((double)waves * c->sm_count);
-    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    if (c->prec == BALM_PREC_TENSOR) {
+      if (eff > best_eff) { best_eff = eff; best = s; }
+      if (eff >= 0.95) break;
+    } else if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = s;
+    }
   }
+  if (const char *e = getenv("BALM_SYRK_SPLITS")) best = std::max(1, std::min(atoi(e), max_splits));  // tuning knob
   c->syrk_splits = best;
   TRY(dev_alloc(&c->syrk_part, (size_t)best * c->syrk_tiles * BALM_SYRK_TILE * BALM_SYRK_TILE));
   if (c->prec == BALM_PREC_TENSOR) TRY(tensor_syrk_init(c));
