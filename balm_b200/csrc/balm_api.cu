@@ -155,6 +155,9 @@ extern "C" int balm_create(balm_ctx **out, int n_poses, int device, int precisio
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  TRY(factor_kernels_setup());
+  TRY(syrk_f64_setup());
+  TRY(ldlt_setup());
   const size_t n = c->n;
   TRY(dev_alloc(&c->poses, 12 * (size_t)c->N));
   TRY(dev_alloc(&c->poses_trial, 12 * (size_t)c->N));

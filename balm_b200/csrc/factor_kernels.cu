@@ -360,12 +360,6 @@ int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1,
               store_stats ? c->stats : nullptr, c->res_part};
   const int psmem = 12 * c->N * (int)sizeof(double);
   const bool in_smem = psmem <= 64 * 1024;  // up to 682 poses; larger windows read the table through L1
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(voxel_stats_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(voxel_stats_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
-  }
   if (in_smem) {
     if (store_stats) voxel_stats_kernel<true, true><<<blocks, STATS_THREADS, psmem, c->stream>>>(a);
     else voxel_stats_kernel<false, true><<<blocks, STATS_THREADS, psmem, c->stream>>>(a);
@@ -466,5 +460,12 @@ int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bo
   else obs_pass_kernel<false, OBS_INT8><<<grid, 128, 0, c->stream>>>(a);
   c->launches += 1;
   CUDA_TRY(cudaGetLastError());
+  return BALM_OK;
+}
+
+// Kernel attributes are per device: set once per context (a process may drive several GPUs).
+int factor_kernels_setup() {
+  CUDA_TRY(cudaFuncSetAttribute(voxel_stats_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(voxel_stats_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   return BALM_OK;
 }

@@ -244,6 +244,9 @@ int launch_pose_update(balm_ctx *c, const double *poses_in, const double *dx, do
 int launch_gauge(balm_ctx *c, double *poses, int mode);
 int launch_synth(balm_ctx *c, int64_t n_voxels, int64_t first_voxel, int pts, double noise, double range,
                  uint64_t seed, const double *poses_gt_dev);
+int factor_kernels_setup();
+int syrk_f64_setup();
+int ldlt_setup();
 int tensor_syrk_init(balm_ctx *c);
 void tensor_syrk_free(balm_ctx *c);
 int tensor_syrk_check(balm_ctx *c);

@@ -507,15 +507,6 @@ static int enqueue_solve(balm_ctx *c) {
 
 int launch_ldlt_solve(balm_ctx *c, double u) {
   const int n = c->n;
-  static bool attr_set2 = false;
-  if (!attr_set2) {
-    CUDA_TRY(cudaFuncSetAttribute(ldl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  2 * NB * (NB + 4) * (int)sizeof(double)));
-    CUDA_TRY(cudaFuncSetAttribute(ldl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  USTAGE * (int)sizeof(double)));
-    CUDA_TRY(cudaFuncSetAttribute(ldl_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
-    attr_set2 = true;
-  }
   if (!c->Xinv) {
     const int npan = (n + NB - 1) / NB;
     CUDA_TRY(cudaMalloc((void **)&c->Xinv, sizeof(double) * (size_t)npan * NB * NB));
@@ -559,5 +550,14 @@ int launch_gauge(balm_ctx *c, double *poses, int mode) {
   gauge_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(poses, c->scal + 4, c->N, mode);
   c->launches += 1;
   CUDA_TRY(cudaGetLastError());
+  return BALM_OK;
+}
+
+int ldlt_setup() {
+  CUDA_TRY(cudaFuncSetAttribute(ldl_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                2 * NB * (NB + 4) * (int)sizeof(double)));
+  CUDA_TRY(cudaFuncSetAttribute(ldl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                USTAGE * (int)sizeof(double)));
+  CUDA_TRY(cudaFuncSetAttribute(ldl_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
   return BALM_OK;
 }

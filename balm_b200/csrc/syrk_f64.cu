@@ -183,11 +183,6 @@ __global__ void assemble_kernel(AsmArgs a) {
 int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch) {
   SyrkArgs a{c->G, rows, c->ldg, c->syrk_nb, c->syrk_tiles, c->syrk_splits, c->syrk_part, first_batch ? 0 : 1};
   const int smem = 2 * STAGE_DOUBLES * (int)sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(syrk_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
   const int items = a.tiles * a.splits;
   const int grid = items < c->sm_count ? items : c->sm_count;
   syrk_f64_kernel<<<grid, SYRK_THREADS, smem, c->stream>>>(a);
@@ -202,5 +197,11 @@ int launch_assemble(balm_ctx *c) {
   assemble_kernel<<<grid, block, 0, c->stream>>>(a);
   c->launches += 1;
   CUDA_TRY(cudaGetLastError());
+  return BALM_OK;
+}
+
+int syrk_f64_setup() {
+  CUDA_TRY(cudaFuncSetAttribute(syrk_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                2 * STAGE_DOUBLES * (int)sizeof(double)));
   return BALM_OK;
 }
