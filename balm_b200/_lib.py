@@ -24,7 +24,8 @@ class Trace(C.Structure):
 class Timings(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("ms_stats", "ms_obs", "ms_slice", "ms_syrk", "ms_assemble",
                                          "ms_allreduce", "ms_solve", "ms_residual", "ms_update")] + \
-               [("launches", C.c_int), ("n_eval", C.c_int), ("n_solve", C.c_int), ("n_residual", C.c_int)]
+               [("launches", C.c_int), ("n_eval", C.c_int), ("n_solve", C.c_int), ("n_residual", C.c_int),
+                ("digit_planes", C.c_int)]
 
 
 class BalmError(RuntimeError):

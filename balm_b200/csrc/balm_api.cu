@@ -116,7 +116,7 @@ static int alloc_workspaces(balm_ctx *c) {
   // every split costs one fp64 partial tile per output tile (written by the SYRK epilogue, read by the assembly):
   // the tensor path (6 ms SYRK) takes the SMALLEST split count that keeps the last wave >= 95 % full and respects
   // the int32 exactness bound (<= 32704 contraction rows per item); the fp64 path (97 ms SYRK) maximises balance.
-  const int min_splits = c->prec == BALM_PREC_TENSOR ? (int)((rows + 32703) / 32704) : 1;
+  const int min_splits = c->prec == BALM_PREC_TENSOR ? (int)((rows + 32575) / 32576) : 1;  // per-item rows (rounded up to 64) stay <= 32640
   for (int s = std::min(min_splits, max_splits); s <= max_splits; s++) {
     const int items = c->syrk_tiles * s;
     const int waves = (items + c->sm_count - 1) / c->sm_count;
@@ -170,6 +170,7 @@ extern "C" int balm_create(balm_ctx **out, int n_poses, int device, int precisio
   TRY(dev_alloc(&c->scal, 16));
   TRY(dev_alloc(&c->flags, 4));
   TRY(dev_alloc(&c->accum, (size_t)BALM_ACC * c->Np));
+  TRY(dev_alloc(&c->accum_batch, (size_t)BALM_ACC * c->Np));
   c->res_blocks = c->sm_count * 24;  // residual partials: one per warp of the stats kernel (3 CTAs x 8 warps per SM)
   TRY(dev_alloc(&c->res_part, (size_t)c->res_blocks));
   CUDA_TRY(cudaMallocHost((void **)&c->h_scal, 16 * sizeof(double)));
@@ -186,7 +187,7 @@ extern "C" int balm_destroy(balm_ctx *c) {
   free_problem(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaFree(c->poses); cudaFree(c->poses_trial); cudaFree(c->H); cudaFree(c->A); cudaFree(c->W);
-  cudaFree(c->dx); cudaFree(c->dvec); cudaFree(c->scal); cudaFree(c->flags); cudaFree(c->accum);
+  cudaFree(c->dx); cudaFree(c->dvec); cudaFree(c->scal); cudaFree(c->flags); cudaFree(c->accum); cudaFree(c->accum_batch);
   cudaFree(c->res_part); cudaFree(c->Xinv); cudaFree(c->dinv); cudaFree(c->sol);
   if (c->solve_graph) cudaGraphExecDestroy((cudaGraphExec_t)c->solve_graph);
   cudaFreeHost(c->h_scal); cudaFreeHost(c->h_flags);

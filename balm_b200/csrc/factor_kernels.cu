@@ -128,7 +128,7 @@ struct ObsArgs {
   const double *sc;     // [ldg] column scales 2^p
   int8_t *Gq;           // [S][rows_alloc][ldg]
   int64_t plane_stride;
-  int S;
+  const int *S_dev;     // digit-plane count chosen on the device by tc_scale_kernel
   // csc
   const int *csc_ptr, *csc_obs, *csc_vox;
 };
@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
   for (int q = 0; q < BALM_ACC; q++) acc[q] = 0.0;
   double cmax[6] = {0, 0, 0, 0, 0, 0};
   double scl[6] = {0, 0, 0, 0, 0, 0};
+  const int S = (MODE == OBS_INT8) ? *a.S_dev : 0;
   if (MODE == OBS_INT8 && active) {
 #pragma unroll
     for (int q = 0; q < 6; q++) scl[q] = __ldg(a.sc + 6 * i + q);
@@ -268,8 +269,8 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
           int8_t *base = a.Gq + (size_t)(3 * (v - a.v0) + rr) * a.ldg + 6 * i;
 #pragma unroll
           for (int kb = 0; kb < 4; kb++) {        // byte kb = digit of weight 256^kb = plane S-1-kb
-            if (kb < a.S) {
-              unsigned short *o16 = reinterpret_cast<unsigned short *>(base + (size_t)(a.S - 1 - kb) * a.plane_stride);
+            if (kb < S) {
+              unsigned short *o16 = reinterpret_cast<unsigned short *>(base + (size_t)(S - 1 - kb) * a.plane_stride);
 #pragma unroll
               for (int h = 0; h < 3; h++)
                 o16[h] = (unsigned short)__byte_perm(D[2 * h], D[2 * h + 1], kb | ((4 + kb) << 4));
@@ -279,8 +280,12 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
       }
       if (MODE != OBS_INT8) {
 #pragma unroll
-        for (int q = 0; q < 6; q++)
+        for (int q = 0; q < 6; q++) {
           cmax[q] = fmax(cmax[q], fmax(fabs(gv[0][q]), fmax(fabs(gv[1][q]), fabs(gv[2][q]))));
+          // exact diagonal of G'^T G': the split-integer SYRK drops the digit pair (S/2,S/2), which is a positive
+          // bias on sums of squares only -- the n diagonal entries are therefore taken from this fp64 sum instead
+          acc[27 + q] += gv[0][q] * gv[0][q] + gv[1][q] * gv[1][q] + gv[2][q] * gv[2][q];
+        }
       }
     }
     if (MODE == OBS_INT8) continue;  // gradient and diagonal blocks were accumulated by the first sweep
@@ -338,12 +343,14 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
   }
 }
 
-__global__ void obs_reduce_kernel(const double *part, int chunks, int total, double *accum, int add) {
+__global__ void obs_reduce_kernel(const double *part, int chunks, int total, double *accum, double *accum_batch,
+                                  int add) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   double s = 0.0;
   for (int c = 0; c < chunks; c++) s += part[(size_t)c * total + e];
   accum[e] = add ? accum[e] + s : s;
+  accum_batch[e] = s;  // this batch only (column concentration of the tensor path)
 }
 
 }  // namespace
@@ -413,7 +420,7 @@ int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bo
   else obs_pass_kernel<false, OBS_FP64><<<grid, 128, 0, c->stream>>>(a);
   const int total = BALM_ACC * c->Np;
   obs_reduce_kernel<<<(total + 255) / 256, 256, 0, c->stream>>>(c->obs_part, chunks, total, c->accum,
-                                                                first_batch ? 0 : 1);
+                                                                c->accum_batch, first_batch ? 0 : 1);
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return BALM_OK;
@@ -431,7 +438,7 @@ int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, 
   else obs_pass_kernel<false, OBS_MAXONLY><<<grid, 128, 0, c->stream>>>(a);
   const int total = BALM_ACC * c->Np;
   obs_reduce_kernel<<<(total + 255) / 256, 256, 0, c->stream>>>(c->obs_part, chunks, total, c->accum,
-                                                                first_batch ? 0 : 1);
+                                                                c->accum_batch, first_batch ? 0 : 1);
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return BALM_OK;
@@ -439,12 +446,13 @@ int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, 
 
 // tensor path, sweep 2: int8 digit planes written directly.
 int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch, const double *sc,
-                    int8_t *Gq, int64_t plane_stride, int S, int64_t rows_padded) {
+                    int8_t *Gq, int64_t plane_stride, const int *S_dev, int S_alloc, int64_t rows_padded) {
   const int64_t nv = v1 - v0;
   if (nv <= 0) return BALM_OK;
   ObsArgs a;
   obs_fill(c, a, poses, v0, v1);
-  a.sc = sc; a.Gq = Gq; a.plane_stride = plane_stride; a.S = S;
+  a.sc = sc; a.Gq = Gq; a.plane_stride = plane_stride; a.S_dev = S_dev;
+  const int S = S_alloc;  // memsets cover every allocated plane
   dim3 grid;
   const int chunks = obs_grid(c, a, nv, grid);
   if (!c->dense) {

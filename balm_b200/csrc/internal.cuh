@@ -7,7 +7,8 @@
 #include "../../include/balm_b200.h"
 
 #define BALM_STATS_STRIDE 20  // doubles per voxel in the stats table
-#define BALM_ACC 27           // per-(pose) accumulators of the observation pass: g(6) + sym 6x6 diag block (21)
+#define BALM_ACC 33           // per-pose accumulators of the observation pass: g(6) + sym 6x6 diag block (21)
+                              // + exact fp64 sums of squares of the 6 G' columns (diagonal of G'^T G')
 #define BALM_NB 64            // LDL^T panel width
 #define BALM_SYRK_TILE 128
 
@@ -67,7 +68,8 @@ struct balm_ctx {
   double *G = nullptr;            // [3*VB][ldg] fp64 scaled factor matrix G' (MN-major: pose index contiguous)
   int obs_chunks = 0;
   double *obs_part = nullptr;     // [obs_chunks][27][Np]
-  double *accum = nullptr;        // [27][Np] reduced g / diag-block accumulators
+  double *accum = nullptr;        // [BALM_ACC][Np] reduced g / diag-block / sum-of-squares accumulators
+  double *accum_batch = nullptr;  // same, current batch only
   int res_blocks = 0;
   double *res_part = nullptr;     // [res_blocks]
   int syrk_splits = 0, syrk_tiles = 0, syrk_nb = 0;
@@ -235,7 +237,7 @@ int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1,
 int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch, const double *sc,
-                    int8_t *Gq, int64_t plane_stride, int S, int64_t rows_padded);
+                    int8_t *Gq, int64_t plane_stride, const int *S_dev, int S_alloc, int64_t rows_padded);
 int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch);
 int launch_assemble(balm_ctx *c);

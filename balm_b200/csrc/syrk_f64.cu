@@ -150,8 +150,9 @@ __global__ void __launch_bounds__(SYRK_THREADS, 1) syrk_f64_kernel(SyrkArgs a) {
 struct AsmArgs {
   const double *part;
   int splits, tiles, nb;
-  const double *accum;  // [27][Np]
+  const double *accum;  // [BALM_ACC][Np]
   int N, Np, n;
+  int exact_diag;       // take the diagonal of G'^T G' from the fp64 sums of squares (tensor path)
   double *H;            // n x n
   double *g;            // n
 };
@@ -169,6 +170,7 @@ __global__ void assemble_kernel(AsmArgs a) {
   for (int sp = 0; sp < a.splits; sp++) s += a.part[(size_t)sp * a.tiles * (TILE * TILE) + off];
   double h = -s;
   const int pi = r / 6, pj = c / 6;
+  if (a.exact_diag && r == c) h = -a.accum[(size_t)(27 + r % 6) * a.Np + pi];
   if (pi == pj) {
     const int rr = r % 6, cc = c % 6;  // rr <= cc
     const int q = 6 + rr * 6 - rr * (rr - 1) / 2 + (cc - rr);
@@ -192,7 +194,8 @@ int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch) {
 }
 
 int launch_assemble(balm_ctx *c) {
-  AsmArgs a{c->syrk_part, c->syrk_splits, c->syrk_tiles, c->syrk_nb, c->accum, c->N, c->Np, c->n, c->H, c->g};
+  AsmArgs a{c->syrk_part, c->syrk_splits, c->syrk_tiles, c->syrk_nb, c->accum, c->N, c->Np, c->n,
+            c->prec == BALM_PREC_TENSOR ? 1 : 0, c->H, c->g};
   dim3 block(32, 8), grid((c->n + 31) / 32, (c->n + 7) / 8);
   assemble_kernel<<<grid, block, 0, c->stream>>>(a);
   c->launches += 1;

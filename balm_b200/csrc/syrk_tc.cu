@@ -34,7 +34,7 @@ constexpr int MAX_STAGES = 6;
 __host__ __device__ constexpr int stage_bytes_for(int S) { return 2 * S * PLANE_TILE_BYTES; }
 __host__ __device__ constexpr int stages_for(int S) { return RING_BYTES / (2 * S * PLANE_TILE_BYTES); }
 constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
-constexpr int MAX_ROWS_PER_ITEM = 32768 - KS;           // S * rows * 2^14 < 2^31
+constexpr int MAX_ROWS_PER_ITEM = 32576;                // S * rows * 2^14 < 2^31 with the 64-row rounding of the k-split
 
 // ---------------- PTX wrappers ----------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,7 +137,8 @@ __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {
 
 struct TcArgs {
   int64_t rows;       // contraction rows of this batch (3 per voxel)
-  int nb, tiles, splits, S;
+  int nb, tiles, splits;
+  const int *S_dev;   // digit-plane count chosen by tc_scale_kernel
   const double *isc;  // [ldq]  256^(S-1) / sc_j
   double *part;       // [splits][tiles][128*128]
   int accumulate;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = a.S;
+  const int S = *a.S_dev;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -353,21 +354,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
   }
 }
 
-// sc_j = 2^p with colmax_j * sc_j in [2^(8S-3), 2^(8S-2));  isc_j = 256^(S-1) / sc_j
-__global__ void tc_scale_kernel(const unsigned long long *colmax_bits, double *sc, double *isc, int ldq, int S) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= ldq) return;
-  const double m = __longlong_as_double((long long)colmax_bits[j]);
-  if (!(m > 0.0) || !(m < 1e300)) {
-    sc[j] = 0.0;
-    isc[j] = 0.0;
-    return;
+// Column scales and the digit-plane count, decided ON THE DEVICE from the current data (one block):
+//   e_j = max|G'_j| / sqrt(sum G'_j^2)  is the concentration of column j (1 = a single dominant entry, ~1/sqrt(rows)
+//   for evenly spread columns); rounding G' to 2^-(8S-2) of the column maximum perturbs H_ij by about
+//   2^-(8S-2) * e * sqrt(H_ii H_jj).  S = 3 is used when that stays below 5e-9 for every column, else S = 4
+//   (forced_S > 0 overrides).  Then sc_j = 2^p with colmax_j * sc_j in [2^(8S-3), 2^(8S-2)), isc_j = 256^(S-1)/sc_j.
+__global__ void __launch_bounds__(1024) tc_scale_kernel(const unsigned long long *colmax_bits, const double *accum_batch,
+                                                        int Np, int n, double *sc, double *isc, int ldq, int forced_S,
+                                                        int *S_dev) {
+  __shared__ double red[32];
+  __shared__ int S_sh;
+  double emax = 0.0;
+  for (int j = threadIdx.x; j < n; j += 1024) {
+    const double m = __longlong_as_double((long long)colmax_bits[j]);
+    const double h = accum_batch[(size_t)(27 + j % 6) * Np + j / 6];
+    if (m > 0.0 && h > 0.0) emax = fmax(emax, m / sqrt(h));
   }
-  int e;
-  frexp(m, &e);  // m = f * 2^e, f in [0.5, 1)  ->  m < 2^e
-  const int p = 8 * S - 2 - e;
-  sc[j] = ldexp(1.0, p);
-  isc[j] = ldexp(1.0, 8 * (S - 1) - p);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = emax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double e = 0.0;
+    for (int w = 0; w < 32; w++) e = fmax(e, red[w]);
+    int S = (e * (1.0 / 4194304.0) <= 5e-9) ? 3 : 4;  // 2^-22 * e
+    if (forced_S > 0) S = forced_S;
+    S_sh = S;
+    *S_dev = S;
+  }
+  __syncthreads();
+  const int S = S_sh;
+  for (int j = threadIdx.x; j < ldq; j += 1024) {
+    const double m = __longlong_as_double((long long)colmax_bits[j]);
+    if (!(m > 0.0) || !(m < 1e300)) {
+      sc[j] = 0.0;
+      isc[j] = 0.0;
+      continue;
+    }
+    int e;
+    frexp(m, &e);  // m = f * 2^e, f in [0.5, 1)  ->  m < 2^e
+    const int p = 8 * S - 2 - e;
+    sc[j] = ldexp(1.0, p);
+    isc[j] = ldexp(1.0, 8 * (S - 1) - p);
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -380,7 +409,9 @@ struct TcState {
   unsigned long long *colmax = nullptr;
   int *err = nullptr;
   int64_t rows_alloc = 0;
-  int S = 4;
+  int forced_S = 0;      // BALM_TC_SLICES override (0 = decided on the device per batch)
+  int *S_dev = nullptr;  // [1]
+  int last_S = 0;        // read back with the error flag (instrumentation)
 };
 
 }  // namespace
@@ -389,19 +420,16 @@ int tensor_syrk_init(balm_ctx *c) {
   tensor_syrk_free(c);
   TcState *st = new TcState();
   c->tmap = st;
-  // Digit planes: the fixed-point rounding of G' (2^-(8S-2) of each column maximum, zero-mean) averages out over
-  // the contraction length like 1/sqrt(rows), while the dropped digit pairs leave a 256^-4 floor for S = 3 and
-  // S = 4 alike (measured at C3: max|dH|/max|H| 2.7e-10 vs 1.9e-10, |d dx| 9e-10 vs 8e-11, contract 1e-6).
-  // So long contractions use 3 planes (6 digit-pair products instead of 10), short ones keep 4.
-  st->S = (3 * c->VB >= 49152) ? 3 : 4;
+  // Digit planes (3 or 4) are chosen per batch on the device (tc_scale_kernel); BALM_TC_SLICES=2..4 forces a count.
   if (const char *e = getenv("BALM_TC_SLICES")) {
     const int v = atoi(e);
-    if (v >= 2 && v <= SMAX) st->S = v;
+    if (v >= 2 && v <= SMAX) st->forced_S = v;
   }
   const int ldq = c->ldg;
   st->rows_alloc = (3 * c->VB + KS - 1) / KS * KS;
-  CUDA_TRY(cudaMalloc((void **)&c->Gq, (size_t)st->S * st->rows_alloc * ldq));
-  CUDA_TRY(cudaMemset(c->Gq, 0, (size_t)st->S * st->rows_alloc * ldq));  // column padding [6N, ldg) stays zero
+  CUDA_TRY(cudaMalloc((void **)&c->Gq, (size_t)SMAX * st->rows_alloc * ldq));
+  CUDA_TRY(cudaMemset(c->Gq, 0, (size_t)SMAX * st->rows_alloc * ldq));  // column padding [6N, ldg) stays zero
+  CUDA_TRY(cudaMalloc((void **)&st->S_dev, sizeof(int)));
   CUDA_TRY(cudaMalloc((void **)&st->sc, sizeof(double) * ldq));
   CUDA_TRY(cudaMalloc((void **)&st->isc, sizeof(double) * ldq));
   CUDA_TRY(cudaMalloc((void **)&st->colmax, sizeof(unsigned long long) * ldq));
@@ -416,7 +444,7 @@ int tensor_syrk_init(balm_ctx *c) {
     balm_set_error("cuTensorMapEncodeTiled not available from the driver");
     return BALM_ERR_CUDA;
   }
-  const cuuint64_t dims[3] = {(cuuint64_t)ldq, (cuuint64_t)st->rows_alloc, (cuuint64_t)st->S};
+  const cuuint64_t dims[3] = {(cuuint64_t)ldq, (cuuint64_t)st->rows_alloc, (cuuint64_t)SMAX};
   const cuuint64_t strides[2] = {(cuuint64_t)ldq, (cuuint64_t)ldq * st->rows_alloc};
   const cuuint32_t box[3] = {TILE, KS, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
@@ -444,7 +472,7 @@ int tensor_syrk_init(balm_ctx *c) {
 void tensor_syrk_free(balm_ctx *c) {
   if (c->tmap) {
     TcState *st = static_cast<TcState *>(c->tmap);
-    cudaFree(st->sc); cudaFree(st->isc); cudaFree(st->colmax); cudaFree(st->err);
+    cudaFree(st->sc); cudaFree(st->isc); cudaFree(st->colmax); cudaFree(st->err); cudaFree(st->S_dev);
     delete st;
     c->tmap = nullptr;
   }
@@ -464,11 +492,13 @@ int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1
   CUDA_TRY(cudaMemsetAsync(st->colmax, 0, sizeof(unsigned long long) * ldq, c->stream));
   int rc = launch_obs_colmax(c, poses, v0, v1, first_batch);
   if (rc != BALM_OK) return rc;
-  tc_scale_kernel<<<(ldq + 255) / 256, 256, 0, c->stream>>>(st->colmax, st->sc, st->isc, ldq, st->S);
-  rc = launch_obs_int8(c, poses, v0, v1, first_batch, st->sc, c->Gq, (int64_t)st->rows_alloc * ldq, st->S, rows_padded);
+  tc_scale_kernel<<<1, 1024, 0, c->stream>>>(st->colmax, c->accum_batch, c->Np, c->n, st->sc, st->isc, ldq,
+                                             st->forced_S, st->S_dev);
+  rc = launch_obs_int8(c, poses, v0, v1, first_batch, st->sc, c->Gq, (int64_t)st->rows_alloc * ldq, st->S_dev, SMAX,
+                       rows_padded);
   if (rc != BALM_OK) return rc;
   CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-  TcArgs a{rows_padded, c->syrk_nb, c->syrk_tiles, c->syrk_splits, st->S, st->isc, c->syrk_part,
+  TcArgs a{rows_padded, c->syrk_nb, c->syrk_tiles, c->syrk_splits, st->S_dev, st->isc, c->syrk_part,
            first_batch ? 0 : 1, st->err, getenv("BALM_TC_COLLECTOR") ? 1 : 0};
   const int items = a.tiles * a.splits;
   const int grid = items < c->sm_count ? items : c->sm_count;
@@ -484,7 +514,9 @@ int tensor_syrk_check(balm_ctx *c) {
   if (!st) return BALM_OK;
   int e = 0;
   CUDA_TRY(cudaMemcpyAsync(&e, st->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(&st->last_S, st->S_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->tm.digit_planes = st->last_S;
   if (e != 0) {
     balm_set_error("tcgen05 SYRK pipeline timed out (mbarrier wait bound exceeded)");
     return BALM_ERR_CUDA;

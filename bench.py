@@ -297,7 +297,7 @@ def main():
             "traffic_note": "dram__bytes_read+write per launch from profiles/r1_tensor_ncu_full_summary.json; algorithmic "
                             "bytes of this kernel = digit planes read once (3 x 3M x ldg B) + fp64 partial tiles written"}
     if args.precision == "tensor":
-        planes = 3 if 3 * M >= 49152 else 4
+        planes = tm["digit_planes"]
         pairs = planes * (planes + 1) // 2
         int8_ops = 2.0 * pairs * 0.5 * (3072 // 128) * (3072 // 128 + 1) * 128 * 128 * 3 * M if N == 500 else None
         roof["digit_planes"] = planes

@@ -74,6 +74,7 @@ typedef struct {
   float ms_stats, ms_obs, ms_slice, ms_syrk, ms_assemble, ms_allreduce, ms_solve, ms_residual, ms_update;
   int launches;   /* kernels launched by the library since balm_reset_counters() */
   int n_eval, n_solve, n_residual;
+  int digit_planes; /* tensor path: int8 digit planes used by the last evaluation (3 or 4, chosen on the device) */
 } balm_timings;
 
 const char *balm_last_error(void);
