@@ -125,20 +125,26 @@ def cpu_sample(n_poses, voxels_total, sample_voxels, threads, obs=None):
     return t_iter, dict(t_eval_sample=t_eval, t_solve=t_solve, t_residual_sample=t_res, scale=scale)
 
 
+def numpy_sample(n_poses, sample_voxels):
+    """benchmark_virtual-shaped sample scene generated with numpy (tests/scenes.py) -- keeps the reference arm free
+    of any balm_b200 code."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenes
+    sc = scenes.make_scene(n_poses=n_poses, n_planes=sample_voxels, pts_size=PTS, point_noise=NOISE, surf_range=RANGE,
+                           seed=SEED)
+    return sc["row_ptr"], sc["pose_idx"], sc["obs10"], sc["coe"], sc["poses_init"]
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path. The reference needs Eigen, PCL and
     ROS, none of which exist in this image (no baseline/_ref, no oracle/_ref), so the arm times the oracle port
     of the reference loop nest (4 threads for the accumulation, 1 for residual and LDL^T, like the reference).
-    Each step = one LM iteration on a bounded voxel sample, extrapolated linearly in M."""
+    Each step = one LM iteration on a bounded voxel sample, extrapolated linearly in M. No balm_b200 code runs."""
     if rank != 0:
         return
     n, m = args.poses, args.voxels
-    sample = args.cpu_sample_voxels
-    import balm_b200
-    c = balm_b200.Context(n, 0, 0)
-    gt, init = c.synth_virtual(sample, 0, PTS, NOISE, RANGE, SEED)
-    data = c.download_voxels() + (init,)
-    c.close()
+    sample = min(args.cpu_sample_voxels, 128)
+    data = numpy_sample(n, sample)
     times = []
     for i in range(args.warmup + args.steps):
         t, detail = cpu_sample(n, m, sample, 4, data)
@@ -150,8 +156,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "ba_iterations_per_sec", "value": val, "unit": "iter/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_iter, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BA LM iteration, {n} poses x {m} plane voxels (benchmark_virtual shape, "
-                               f"{PTS} pts/obs), CPU oracle port", "poses": n, "voxels": m},
+        "config": {"workload": f"BASELINE C3: BA LM iteration, {n} poses x {m} plane voxels (benchmark_virtual shape, "
+                               f"{PTS} pts/obs), CPU oracle port of the reference loop nest", "poses": n, "voxels": m},
         "cpu_baseline": {"value": val, "unit": "iter/s", "cores": 4, "kind": "port",
                          "sample": f"{sample} of {m} voxels at {n} poses, O(M) passes scaled x{m / sample:.0f}; "
                                    f"LDL^T n={6 * n} at full size; accumulation 4 threads, rest 1 thread",
