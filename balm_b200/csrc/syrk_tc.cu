@@ -19,6 +19,7 @@
 //   warps 2-9: epilogue      -- tcgen05.ld 32x32b of the S accumulators, fp64 Horner combine, column scales,
 //              fp64 partial tile to global (same partial layout as the fp64 path -> same assemble kernel)
 #include <cuda.h>
+#include <vector>
 #include "internal.cuh"
 
 namespace {
@@ -72,6 +73,32 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// multicast variant: the box lands at the same shared-memory offset in every CTA of cta_mask and completes the
+// transaction bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_3d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// commit that arrives on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -144,6 +171,17 @@ struct TcArgs {
   int accumulate;
   int *err;
   int collector;
+  // 2-CTA cluster variant: work list of tile pairs (x: bi0 | bj0<<8 | bi1<<16 | bj1<<24, y: flags 1=share B, 2=dup)
+  const int2 *pairs;
+  int n_pairs;
+};
+
+struct ItemInfo {
+  int bi, bj, sp, t;
+  bool a_from_b;   // A operand = the (shared) B block (diagonal tile of a B-sharing pair): A is not loaded
+  bool b_from_a;   // B operand = own A block (diagonal tile, not sharing)
+  bool share;      // B block arrives half from this CTA, half from the peer (TMA multicast)
+  bool store;      // false for the duplicate of an unpaired tile
 };
 
 __device__ __forceinline__ void tile_coords_tc(int t, int nb, int &bi, int &bj) {
@@ -153,13 +191,39 @@ __device__ __forceinline__ void tile_coords_tc(int t, int nb, int &bi, int &bj) 
   bj = r + rem;
 }
 
+template <bool CLUSTER>
+__device__ __forceinline__ ItemInfo decode_item(const TcArgs &a, int work, uint32_t rank) {
+  ItemInfo it;
+  if (!CLUSTER) {
+    it.t = work % a.tiles;
+    it.sp = work / a.tiles;
+    tile_coords_tc(it.t, a.nb, it.bi, it.bj);
+    it.a_from_b = false;
+    it.b_from_a = (it.bi == it.bj);
+    it.share = false;
+    it.store = true;
+  } else {
+    const int2 pr = a.pairs[work % a.n_pairs];
+    it.sp = work / a.n_pairs;
+    it.bi = (pr.x >> (rank ? 16 : 0)) & 255;
+    it.bj = (pr.x >> (rank ? 24 : 8)) & 255;
+    it.t = it.bi * a.nb - it.bi * (it.bi - 1) / 2 + (it.bj - it.bi);
+    it.share = (pr.y & 1) != 0;
+    it.a_from_b = it.share && it.bi == it.bj;
+    it.b_from_a = !it.share && it.bi == it.bj;
+    it.store = !((pr.y & 2) && rank == 1);
+  }
+  return it;
+}
+
 // The MMA issue loop runs in ONE thread, so its scalar overhead per UTCIMMA bounds the tensor pipe: everything
 // that can be a compile-time constant is (digit-plane count, the (s,t) pair list, descriptor offsets), and a
 // descriptor is the stage's base word plus a constant (the 14-bit start-address field never carries).
-template <int S, bool COLLECT>
+template <int S, bool COLLECT, bool CLUSTER>
 __device__ __forceinline__ void mma_issue_loop(const TcArgs &a, uint8_t *stage_base, uint64_t *full_bar,
                                                uint64_t *empty_bar, uint64_t *tmem_full, uint64_t *tmem_empty,
-                                               uint32_t tmem_base, int n_items, int64_t per) {
+                                               uint32_t tmem_base, int n_items, int64_t per, int first, int stride,
+                                               uint32_t rank) {
   constexpr uint32_t idesc = make_idesc_i8(TILE, TILE);
   constexpr uint32_t PLANE_U = PLANE_TILE_BYTES >> 4;     // descriptor units (16 B) between digit planes
   constexpr uint32_t KK_U = (UMMA_K * TILE) >> 4;         // ... between K=32 sub-steps
@@ -169,23 +233,23 @@ __device__ __forceinline__ void mma_issue_loop(const TcArgs &a, uint8_t *stage_b
   int st = 0;
   uint32_t ph = 0, n_done = 0;
   bool alive = true;
-  for (int item = blockIdx.x; alive && item < n_items; item += gridDim.x, n_done++) {
-    const int t = item % a.tiles, sp = item / a.tiles;
-    int bi, bj;
-    tile_coords_tc(t, a.nb, bi, bj);
-    const int64_t k_begin = (int64_t)sp * per;
+  for (int item = first; alive && item < n_items; item += stride, n_done++) {
+    const ItemInfo info = decode_item<CLUSTER>(a, item, rank);
+    const int64_t k_begin = (int64_t)info.sp * per;
     int64_t k_end = k_begin + per;
     if (k_end > a.rows) k_end = a.rows;
     const int nsteps = k_end > k_begin ? (int)((k_end - k_begin + KS - 1) / KS) : 0;
-    const uint32_t b_off = (bi == bj) ? 0u : S * PLANE_U;
+    const uint32_t a_off = info.a_from_b ? S * PLANE_U : 0u;
+    const uint32_t b_off = info.b_from_a ? 0u : S * PLANE_U;
     // accumulators must have been drained by the epilogue of the previous item
     if (!__all_sync(0xffffffffu, mbar_wait(tmem_empty, (n_done & 1) ^ 1, a.err))) break;
     tc_fence_after();
     for (int ks = 0; ks < nsteps; ks++) {
       if (!__all_sync(0xffffffffu, mbar_wait(&full_bar[st], ph, a.err))) { alive = false; break; }
       tc_fence_after();
-      const uint32_t lo_a = desc_lo_fixed + ((smem_u32(stage_base + st * sbytes) & 0x3FFFF) >> 4);
-      const uint32_t lo_b = lo_a + b_off;
+      const uint32_t lo_0 = desc_lo_fixed + ((smem_u32(stage_base + st * sbytes) & 0x3FFFF) >> 4);
+      const uint32_t lo_a = lo_0 + a_off;
+      const uint32_t lo_b = lo_0 + b_off;
       const uint32_t acc0 = ks > 0 ? 1u : 0u;
       if (elect_one()) {
 #pragma unroll
@@ -207,7 +271,9 @@ __device__ __forceinline__ void mma_issue_loop(const TcArgs &a, uint8_t *stage_b
             }
           }
         }
-        tc_commit(&empty_bar[st]);  // frees the smem stage once these MMAs have read it
+        // frees the smem stage once these MMAs have read it (in both CTAs of a pair: the peer multicasts into it)
+        if (CLUSTER) tc_commit_mc(&empty_bar[st], 3);
+        else tc_commit(&empty_bar[st]);
       }
       __syncwarp();
       if (++st == nst) { st = 0; ph ^= 1; }
@@ -217,7 +283,8 @@ __device__ __forceinline__ void mma_issue_loop(const TcArgs &a, uint8_t *stage_b
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+template <bool CLUSTER>
+__device__ __forceinline__ void syrk_tc_body(const CUtensorMap &tmap, const CUtensorMap &tmap_half, const TcArgs &a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte aligned stage ring, then barriers
   uint8_t *stage_base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -231,7 +298,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
   const int S = *a.S_dev;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < MAX_STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < MAX_STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CLUSTER ? 2 : 1); }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -244,8 +311,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t rank = CLUSTER ? cluster_ctarank() : 0u;
+  if (CLUSTER) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into them
 
-  const int n_items = a.tiles * a.splits;
+  const int n_items = (CLUSTER ? a.n_pairs : a.tiles) * a.splits;
+  const int first = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int stride = CLUSTER ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int64_t per = ((a.rows + a.splits - 1) / a.splits + KS - 1) / KS * KS;
 
   if (warp == 0) {
@@ -256,23 +327,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
       int st = 0;
       uint32_t ph = 0;
       bool alive = true;
-      for (int item = blockIdx.x; alive && item < n_items; item += gridDim.x) {
-        const int t = item % a.tiles, sp = item / a.tiles;
-        int bi, bj;
-        tile_coords_tc(t, a.nb, bi, bj);
-        const int64_t k_begin = (int64_t)sp * per;
+      for (int item = first; alive && item < n_items; item += stride) {
+        const ItemInfo info = decode_item<CLUSTER>(a, item, rank);
+        const int64_t k_begin = (int64_t)info.sp * per;
         int64_t k_end = k_begin + per;
         if (k_end > a.rows) k_end = a.rows;
         const int nsteps = k_end > k_begin ? (int)((k_end - k_begin + KS - 1) / KS) : 0;
-        const bool diag = (bi == bj);
+        const bool load_a = !info.a_from_b, load_b = !info.b_from_a;
         for (int ks = 0; ks < nsteps; ks++) {
           if (!mbar_wait(&empty_bar[st], ph ^ 1, a.err)) { alive = false; break; }
           uint8_t *sb = stage_base + st * sbytes;
-          mbar_expect_tx(&full_bar[st], (diag ? 1 : 2) * S * PLANE_TILE_BYTES);
+          mbar_expect_tx(&full_bar[st], ((load_a ? 1 : 0) + (load_b ? 1 : 0)) * S * PLANE_TILE_BYTES);
           const int krow = (int)(k_begin + (int64_t)ks * KS);
           for (int s = 0; s < S; s++) {
-            tma_load_3d(sb + s * PLANE_TILE_BYTES, &tmap, &full_bar[st], bi * TILE, krow, s);
-            if (!diag) tma_load_3d(sb + (S + s) * PLANE_TILE_BYTES, &tmap, &full_bar[st], bj * TILE, krow, s);
+            if (load_a) tma_load_3d(sb + s * PLANE_TILE_BYTES, &tmap, &full_bar[st], info.bi * TILE, krow, s);
+            if (load_b) {
+              if (CLUSTER && info.share) {
+                // half of the K rows of the shared B block from each CTA of the pair, multicast to both
+                tma_load_3d_mc(sb + (S + s) * PLANE_TILE_BYTES + rank * (KS / 2) * TILE, &tmap_half, &full_bar[st],
+                               info.bj * TILE, krow + (int)rank * (KS / 2), s, 3);
+              } else {
+                tma_load_3d(sb + (S + s) * PLANE_TILE_BYTES, &tmap, &full_bar[st], info.bj * TILE, krow, s);
+              }
+            }
           }
           if (++st == nst) { st = 0; ph ^= 1; }
         }
@@ -280,15 +357,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+#define BALM_ISSUE(SS, CC) mma_issue_loop<SS, CC, CLUSTER>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per, first, stride, rank)
     if (a.collector) {
-      if (S == 4) mma_issue_loop<4, true>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
-      else if (S == 3) mma_issue_loop<3, true>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
-      else mma_issue_loop<2, true>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
+      if (S == 4) BALM_ISSUE(4, true);
+      else if (S == 3) BALM_ISSUE(3, true);
+      else BALM_ISSUE(2, true);
     } else {
-      if (S == 4) mma_issue_loop<4, false>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
-      else if (S == 3) mma_issue_loop<3, false>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
-      else mma_issue_loop<2, false>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per);
+      if (S == 4) BALM_ISSUE(4, false);
+      else if (S == 3) BALM_ISSUE(3, false);
+      else BALM_ISSUE(2, false);
     }
+#undef BALM_ISSUE
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;                // TMEM lane quadrant this warp may access
@@ -296,10 +375,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
     const int row = quad * 32 + lane;         // tile row held by this thread
     uint32_t n_done = 0;
     const double inv256 = 1.0 / 256.0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, n_done++) {
-      const int t = item % a.tiles, sp = item / a.tiles;
-      int bi, bj;
-      tile_coords_tc(t, a.nb, bi, bj);
+    for (int item = first; item < n_items; item += stride, n_done++) {
+      const ItemInfo info = decode_item<CLUSTER>(a, item, rank);
+      const int t = info.t, sp = info.sp, bi = info.bi, bj = info.bj;
       const int64_t k_begin = (int64_t)sp * per;
       const bool empty_item = k_begin >= a.rows;
       if (!mbar_wait(tmem_full, n_done & 1, a.err)) break;
@@ -337,7 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
             w.x += old.x;
             w.y += old.y;
           }
-          *p = w;
+          if (info.store) *p = w;
         }
       }
       tc_fence_before();
@@ -348,10 +426,261 @@ __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();  // neither CTA leaves while the peer may still multicast into it / commit to it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512));
   }
+}
+
+// ====================================================================================================
+// cta_group::2 variant: the two SMs of a cluster issue ONE 256 x 128 x 32 MMA per digit pair. CTA r holds the 128
+// rows of its own A block (tile (bi_r, bj)) and HALF of the shared B block (64 of its 128 columns), so each SM reads
+// 6 KB of operands per MMA instead of 8 KB and receives 25 % fewer TMA bytes -- shared-memory bandwidth is what bounds
+// the 1-SM kernel. The leader (rank 0) issues all MMAs; both CTAs load (signalling the leader's full barrier), both
+// drain their own 128 TMEM lanes.
+// ====================================================================================================
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0
+constexpr int BHALF_TILE_BYTES = KS * (TILE / 2);  // 4096: one plane of this CTA's half of the B block, one stage
+__host__ __device__ constexpr int stage2_bytes_for(int S) { return S * (PLANE_TILE_BYTES + BHALF_TILE_BYTES); }
+__host__ __device__ constexpr int stages2_for(int S) { return RING_BYTES / stage2_bytes_for(S) > MAX_STAGES ? MAX_STAGES : RING_BYTES / stage2_bytes_for(S); }
+
+__device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *map, uint64_t *leader_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(leader_bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mc(uint64_t *bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {  // arrive on the barrier at this offset in CTA rank 0
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+#define BALM_MMA_I8_2SM(QUAL)                                                                \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                            \
+               "tcgen05.mma.cta_group::2.kind::i8" QUAL " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), \
+               "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)                         \
+               : "memory")
+template <int USAGE>
+__device__ __forceinline__ void tc_mma_i8_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if constexpr (USAGE == 1) BALM_MMA_I8_2SM(".collector::a::fill");
+  else if constexpr (USAGE == 2) BALM_MMA_I8_2SM(".collector::a::use");
+  else if constexpr (USAGE == 3) BALM_MMA_I8_2SM(".collector::a::lastuse");
+  else BALM_MMA_I8_2SM("");
+}
+// MN-major, SWIZZLE_64B: 64 contiguous bytes along N per k row, 8 k rows per 512-byte atom, SBO = next 8 k rows
+__device__ __forceinline__ uint64_t make_desc_mn_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((BHALF_TILE_BYTES >> 4) & 0x3FFF) << 16;  // LBO (unused: one 64-byte block along N)
+  d |= (uint64_t)((512 >> 4) & 0x3FFF) << 32;               // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                                   // SWIZZLE_64B
+  return d;
+}
+
+template <int S>
+__device__ __forceinline__ void mma_issue_loop_2sm(const TcArgs &a, uint8_t *stage_base, uint64_t *full_bar,
+                                                   uint64_t *empty_bar, uint64_t *tmem_full, uint64_t *tmem_empty,
+                                                   uint32_t tmem_base, int n_items, int64_t per, int first, int stride) {
+  constexpr uint32_t idesc = make_idesc_i8(2 * TILE, TILE);  // M = 256 across the pair, N = 128
+  constexpr uint32_t PLANE_U = PLANE_TILE_BYTES >> 4, BPLANE_U = BHALF_TILE_BYTES >> 4;
+  constexpr uint32_t KK_A = (UMMA_K * TILE) >> 4, KK_B = (UMMA_K * (TILE / 2)) >> 4;
+  const uint64_t hi_a = make_desc_mn_sw128(0) & 0xFFFFFFFF00000000ull, hi_b = make_desc_mn_sw64(0) & 0xFFFFFFFF00000000ull;
+  const uint32_t fx_a = (uint32_t)(make_desc_mn_sw128(0) & 0xFFFFFFFFull), fx_b = (uint32_t)(make_desc_mn_sw64(0) & 0xFFFFFFFFull);
+  constexpr int nst = stages2_for(S), sbytes = stage2_bytes_for(S);
+  int st = 0;
+  uint32_t ph = 0, n_done = 0;
+  bool alive = true;
+  for (int item = first; alive && item < n_items; item += stride, n_done++) {
+    const int sp = item / a.n_pairs;
+    const int64_t k_begin = (int64_t)sp * per;
+    int64_t k_end = k_begin + per;
+    if (k_end > a.rows) k_end = a.rows;
+    const int nsteps = k_end > k_begin ? (int)((k_end - k_begin + KS - 1) / KS) : 0;
+    if (!__all_sync(0xffffffffu, mbar_wait(tmem_empty, (n_done & 1) ^ 1, a.err))) break;  // both CTAs drained
+    tc_fence_after();
+    for (int ks = 0; ks < nsteps; ks++) {
+      if (!__all_sync(0xffffffffu, mbar_wait(&full_bar[st], ph, a.err))) { alive = false; break; }
+      tc_fence_after();
+      const uint32_t base = (smem_u32(stage_base + st * sbytes) & 0x3FFFF) >> 4;
+      const uint32_t lo_a = fx_a + base, lo_b = fx_b + base + S * PLANE_U;
+      const uint32_t acc0 = ks > 0 ? 1u : 0u;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < KS / UMMA_K; kk++) {
+#pragma unroll
+          for (int s = 0; s < S; s++) {
+            const uint64_t da = hi_a | (uint64_t)(lo_a + s * PLANE_U + kk * KK_A);
+#pragma unroll
+            for (int tt = 0; tt + s < S; tt++) {
+              const uint64_t db = hi_b | (uint64_t)(lo_b + tt * BPLANE_U + kk * KK_B);
+              const uint32_t acc = (s > 0 || kk > 0) ? 1u : acc0;
+              if (S - s == 1) tc_mma_i8_2sm<0>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+              else if (tt == 0) tc_mma_i8_2sm<1>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+              else if (tt == S - s - 1) tc_mma_i8_2sm<3>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+              else tc_mma_i8_2sm<2>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+            }
+          }
+        }
+        tc_commit_2sm_mc(&empty_bar[st], 3);  // frees this stage in both CTAs
+      }
+      __syncwarp();
+      if (++st == nst) { st = 0; ph ^= 1; }
+    }
+    if (alive && elect_one()) tc_commit_2sm_mc(tmem_full, 3);  // accumulators complete in both CTAs
+    __syncwarp();
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    syrk_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b64, TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *stage_base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_base + RING_BYTES);
+  uint64_t *empty_bar = full_bar + MAX_STAGES;
+  uint64_t *tmem_full = empty_bar + MAX_STAGES;
+  uint64_t *tmem_empty = tmem_full + 1;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = *a.S_dev;
+  const uint32_t rank = cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 16);  // 8 epilogue warps of each CTA arrive on the leader's barrier
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_ptr)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  cluster_sync_all();
+
+  const int n_items = a.n_pairs * a.splits;
+  const int first = (int)(blockIdx.x >> 1), stride = (int)(gridDim.x >> 1);
+  const int64_t per = ((a.rows + a.splits - 1) / a.splits + KS - 1) / KS * KS;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; transactions complete on the leader's full barrier) ==========
+    if (lane == 0) {
+      const int nst = stages2_for(S), sbytes = stage2_bytes_for(S);
+      int st = 0;
+      uint32_t ph = 0;
+      bool alive = true;
+      for (int item = first; alive && item < n_items; item += stride) {
+        const int2 pr = a.pairs[item % a.n_pairs];
+        const int sp = item / a.n_pairs;
+        const int bi = (pr.x >> (rank ? 16 : 0)) & 255, bj = (pr.x >> 8) & 255;
+        const int64_t k_begin = (int64_t)sp * per;
+        int64_t k_end = k_begin + per;
+        if (k_end > a.rows) k_end = a.rows;
+        const int nsteps = k_end > k_begin ? (int)((k_end - k_begin + KS - 1) / KS) : 0;
+        for (int ks = 0; ks < nsteps; ks++) {
+          if (!mbar_wait(&empty_bar[st], ph ^ 1, a.err)) { alive = false; break; }
+          uint8_t *sb = stage_base + st * sbytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[st], 2 * sbytes);  // bytes of BOTH CTAs land on the leader's barrier
+          const int krow = (int)(k_begin + (int64_t)ks * KS);
+          for (int s = 0; s < S; s++) {
+            tma_load_3d_2sm(sb + s * PLANE_TILE_BYTES, &tmap, &full_bar[st], bi * TILE, krow, s);
+            tma_load_3d_2sm(sb + S * PLANE_TILE_BYTES + s * BHALF_TILE_BYTES, &tmap_b64, &full_bar[st],
+                            bj * TILE + (int)rank * (TILE / 2), krow, s);
+          }
+          if (++st == nst) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: leader CTA only =====================
+    if (rank == 0) {
+      if (S == 4) mma_issue_loop_2sm<4>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per, first, stride);
+      else if (S == 3) mma_issue_loop_2sm<3>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per, first, stride);
+      else mma_issue_loop_2sm<2>(a, stage_base, full_bar, empty_bar, tmem_full, tmem_empty, tmem_base, n_items, per, first, stride);
+    }
+  } else {
+    // ===================== epilogue: each CTA drains its own 128 TMEM lanes =====================
+    const int quad = warp & 3, half = (warp - 2) >> 2, row = quad * 32 + lane;
+    uint32_t n_done = 0;
+    const double inv256 = 1.0 / 256.0;
+    for (int item = first; item < n_items; item += stride, n_done++) {
+      const int2 pr = a.pairs[item % a.n_pairs];
+      const int sp = item / a.n_pairs;
+      const int bi = (pr.x >> (rank ? 16 : 0)) & 255, bj = (pr.x >> 8) & 255;
+      const bool store = !((pr.y & 2) && rank == 1);
+      const int t = bi <= bj ? bi * a.nb - bi * (bi - 1) / 2 + (bj - bi) : 0;
+      const int64_t k_begin = (int64_t)sp * per;
+      const bool empty_item = k_begin >= a.rows;
+      if (!mbar_wait(tmem_full, n_done & 1, a.err)) break;
+      tc_fence_after();
+      double *out = a.part + ((size_t)sp * a.tiles + t) * (TILE * TILE) + (size_t)row * TILE;
+      const double isc_row = __ldg(a.isc + bi * TILE + row);
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int c0 = half * (TILE / 2); c0 < (half + 1) * (TILE / 2); c0 += 16) {
+        double val[16];
+        if (empty_item) {
+#pragma unroll
+          for (int q = 0; q < 16; q++) val[q] = 0.0;
+        } else {
+          int32_t v[16];
+          tc_ld16(lane_addr + (S - 1) * TILE + c0, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 16; q++) val[q] = (double)v[q];
+          for (int d = S - 2; d >= 0; d--) {
+            tc_ld16(lane_addr + d * TILE + c0, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 16; q++) val[q] = val[q] * inv256 + (double)v[q];
+          }
+        }
+        if (store) {
+#pragma unroll
+          for (int q = 0; q < 16; q += 2) {
+            const double2 sc = *reinterpret_cast<const double2 *>(a.isc + bj * TILE + c0 + q);
+            double2 w = make_double2(val[q] * isc_row * sc.x, val[q + 1] * isc_row * sc.y);
+            double2 *p = reinterpret_cast<double2 *>(out + c0 + q);
+            if (a.accumulate) {
+              const double2 old = *p;
+              w.x += old.x;
+              w.y += old.y;
+            }
+            *p = w;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tmem_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+  syrk_tc_body<false>(tmap, tmap, a);
+}
+
+// 2-CTA cluster variant: the two CTAs of a cluster compute two tiles of the same block column and share the B block
+// (each loads half of its K rows and TMA-multicasts them to both), which cuts the L2->SM operand traffic by 25 %.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    syrk_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half, TcArgs a) {
+  syrk_tc_body<true>(tmap, tmap_half, a);
 }
 
 // Column scales and the digit-plane count, decided ON THE DEVICE from the current data (one block):
@@ -405,6 +734,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 struct TcState {
   CUtensorMap map;
+  CUtensorMap map_half;     // box {128, KS/2, 1}: half-stage loads of the pair kernel
+  int2 *pairs = nullptr;    // device work list of tile pairs
+  int n_pairs = 0;
+  bool use_pairs = false;
+  CUtensorMap map_b64;      // box {64, KS, 1}, 64-byte swizzle: this CTA's half of the B block (2-SM kernel)
+  int2 *pairs2 = nullptr;   // work list of the 2-SM kernel (every pair shares its B block)
+  int n_pairs2 = 0;
+  bool use_2sm = false;
   double *sc = nullptr, *isc = nullptr;
   unsigned long long *colmax = nullptr;
   int *err = nullptr;
@@ -455,6 +792,54 @@ int tensor_syrk_init(balm_ctx *c) {
     balm_set_error("cuTensorMapEncodeTiled failed");
     return BALM_ERR_CUDA;
   }
+  const cuuint32_t box_half[3] = {TILE, KS / 2, 1};
+  if (encode(&st->map_half, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->Gq, dims, strides, box_half, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    balm_set_error("cuTensorMapEncodeTiled (half box) failed");
+    return BALM_ERR_CUDA;
+  }
+  {  // work list of the pair kernel: per block column bj, consecutive rows (bi, bi+1) share the B block bj;
+     // the leftover tile of an odd column is paired with another leftover (no sharing) or duplicated
+    const int nb = c->syrk_nb;
+    std::vector<int2> pairs;
+    std::vector<int> solo;
+    for (int bj = 0; bj < nb; bj++) {
+      int bi = 0;
+      for (; bi + 1 <= bj; bi += 2) pairs.push_back(make_int2(bi | (bj << 8) | ((bi + 1) << 16) | (bj << 24), 1));
+      if (bi <= bj) solo.push_back(bi | (bj << 8));
+    }
+    for (size_t i = 0; i + 1 < solo.size(); i += 2) pairs.push_back(make_int2(solo[i] | (solo[i + 1] << 16), 0));
+    if (solo.size() & 1) pairs.push_back(make_int2(solo.back() | (solo.back() << 16), 2));
+    st->n_pairs = (int)pairs.size();
+    CUDA_TRY(cudaMalloc((void **)&st->pairs, sizeof(int2) * pairs.size()));
+    CUDA_TRY(cudaMemcpy(st->pairs, pairs.data(), sizeof(int2) * pairs.size(), cudaMemcpyHostToDevice));
+    const char *e = getenv("BALM_TC_PAIR");
+    st->use_pairs = (e ? atoi(e) != 0 : false) && nb < 256 && (c->sm_count % 2 == 0);
+    // 2-SM list: rows (bi, bi+1) of block column bj; the lone diagonal tile of an even column is paired with the
+    // below-diagonal tile (bj+1, bj), whose result is discarded (flag 2)
+    std::vector<int2> p2;
+    for (int bj = 0; bj < nb; bj++) {
+      int bi = 0;
+      for (; bi + 1 <= bj; bi += 2) p2.push_back(make_int2(bi | (bj << 8) | ((bi + 1) << 16) | (bj << 24), 1));
+      if (bi <= bj) {
+        const int other = bi + 1 < nb ? bi + 1 : bi;  // last column: duplicate the tile itself
+        p2.push_back(make_int2(bi | (bj << 8) | (other << 16) | (bj << 24), 1 | 2));
+      }
+    }
+    st->n_pairs2 = (int)p2.size();
+    CUDA_TRY(cudaMalloc((void **)&st->pairs2, sizeof(int2) * p2.size()));
+    CUDA_TRY(cudaMemcpy(st->pairs2, p2.data(), sizeof(int2) * p2.size(), cudaMemcpyHostToDevice));
+    const cuuint32_t box_b64[3] = {TILE / 2, KS, 1};
+    if (encode(&st->map_b64, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->Gq, dims, strides, box_b64, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      balm_set_error("cuTensorMapEncodeTiled (64-byte box) failed");
+      return BALM_ERR_CUDA;
+    }
+    const char *e2 = getenv("BALM_TC_2SM");
+    st->use_2sm = (e2 ? atoi(e2) != 0 : true) && nb < 256 && (c->sm_count % 2 == 0);
+  }
   // int32 exactness bound: every (tile, split) item contracts at most MAX_ROWS_PER_ITEM rows
   const int64_t rows = 3 * c->VB;
   const int min_splits = (int)((rows + MAX_ROWS_PER_ITEM - 1) / MAX_ROWS_PER_ITEM);
@@ -466,13 +851,15 @@ int tensor_syrk_init(balm_ctx *c) {
   }
   const int smem = RING_BYTES + 1024 + 256;
   CUDA_TRY(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(syrk_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(syrk_tc_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return BALM_OK;
 }
 
 void tensor_syrk_free(balm_ctx *c) {
   if (c->tmap) {
     TcState *st = static_cast<TcState *>(c->tmap);
-    cudaFree(st->sc); cudaFree(st->isc); cudaFree(st->colmax); cudaFree(st->err); cudaFree(st->S_dev);
+    cudaFree(st->sc); cudaFree(st->isc); cudaFree(st->colmax); cudaFree(st->err); cudaFree(st->S_dev); cudaFree(st->pairs); cudaFree(st->pairs2);
     delete st;
     c->tmap = nullptr;
   }
@@ -499,11 +886,32 @@ int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1
   if (rc != BALM_OK) return rc;
   CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
   TcArgs a{rows_padded, c->syrk_nb, c->syrk_tiles, c->syrk_splits, st->S_dev, st->isc, c->syrk_part,
-           first_batch ? 0 : 1, st->err, getenv("BALM_TC_COLLECTOR") ? 1 : 0};
-  const int items = a.tiles * a.splits;
-  const int grid = items < c->sm_count ? items : c->sm_count;
+           first_batch ? 0 : 1, st->err, getenv("BALM_TC_NO_COLLECTOR") ? 0 : 1, st->pairs, st->n_pairs};
   const int smem = RING_BYTES + 1024 + 256;
-  syrk_tc_kernel<<<grid, TC_THREADS, smem, c->stream>>>(st->map, a);
+  if (st->use_2sm) {
+    a.pairs = st->pairs2;
+    a.n_pairs = st->n_pairs2;
+    const int items = a.n_pairs * a.splits;
+    int clusters = c->sm_count / 2;
+    if (items < clusters) clusters = items;
+    syrk_tc_2sm_kernel<<<2 * clusters, TC_THREADS, smem, c->stream>>>(st->map, st->map_b64, a);
+    if (cudaGetLastError() != cudaSuccess) {  // cluster launch not possible here: fall back to the 1-SM kernel for good
+      st->use_2sm = false;
+      a.pairs = st->pairs;
+      a.n_pairs = st->n_pairs;
+      const int items1 = a.tiles * a.splits;
+      syrk_tc_kernel<<<items1 < c->sm_count ? items1 : c->sm_count, TC_THREADS, smem, c->stream>>>(st->map, a);
+    }
+  } else if (st->use_pairs) {
+    const int items = a.n_pairs * a.splits;
+    int clusters = c->sm_count / 2;
+    if (items < clusters) clusters = items;
+    syrk_tc_pair_kernel<<<2 * clusters, TC_THREADS, smem, c->stream>>>(st->map, st->map_half, a);
+  } else {
+    const int items = a.tiles * a.splits;
+    const int grid = items < c->sm_count ? items : c->sm_count;
+    syrk_tc_kernel<<<grid, TC_THREADS, smem, c->stream>>>(st->map, a);
+  }
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return BALM_OK;
