@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 3) voxel_stats_kernel(StatsArgs
       const long long sB = hasB ? sA + 32 : sA;
       double oa[10], ob[10];
 #pragma unroll
-      for (int c = 0; c < 10; c++) { oa[c] = __ldg(a.obs + c * a.Kp + sA); ob[c] = __ldg(a.obs + c * a.Kp + sB); }
+      for (int c = 0; c < 10; c++) { oa[c] = ld_stream(a.obs + c * a.Kp + sA); ob[c] = ld_stream(a.obs + c * a.Kp + sB); }
       const int pa = __ldg(a.pose_idx + sA), pb = __ldg(a.pose_idx + sB);
       double r[9], p[3];
       load_pose_any<SMEM_POSES>(ptab + 12 * pa, r, p);
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
       else s = a.csc_obs[t];
       if (!DENSE || active) {
 #pragma unroll
-        for (int c = 0; c < 10; c++) dst[c] = __ldg(a.obs + c * a.Kp + s);
+        for (int c = 0; c < 10; c++) dst[c] = ld_stream(a.obs + c * a.Kp + s);
       }
     }
   };

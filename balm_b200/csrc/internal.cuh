@@ -142,6 +142,13 @@ __device__ __forceinline__ void load_pose(const double *__restrict__ pose12, dou
   p[2] = __ldg(pose12 + 11);
 }
 
+// streaming load: read-only path, do not allocate in L1 (the observations are read exactly once per kernel)
+__device__ __forceinline__ double ld_stream(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
+  return v;
+}
+
 template <bool PLAIN>
 __device__ __forceinline__ void load_pose_any(const double *pose12, double *r, double *p) {
   if (PLAIN) {  // shared-memory table
