@@ -8,7 +8,6 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
-#include <mutex>
 #include <vector>
 #include "internal.cuh"
 
@@ -543,7 +542,6 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
   CUDA_TRY(cudaMemcpyAsync(c->poses, poses12, pbytes, cudaMemcpyHostToDevice, c->stream));
   double u = o->u0, v = o->v0, r1 = 0, r2 = 0;
   bool calc_hess = true;
-  float ms_update = 0;
   for (int it = 0; it < o->max_iter; it++) {
     if (calc_hess) {
       TRY(evaluate_dev(c, c->poses, 0, c->M, o->hess_includes_fix != 0));
@@ -583,7 +581,6 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
   if (o->gauge_mode == 0 || o->gauge_mode == 1) TRY(launch_gauge(c, c->poses, o->gauge_mode));
   CUDA_TRY(cudaMemcpyAsync(poses12, c->poses, pbytes, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  (void)ms_update;
   return BALM_OK;
 }
 

@@ -25,7 +25,6 @@ void balm_set_error(const std::string &s);
     }                                                                                         \
   } while (0)
 
-struct NcclDyn;  // nccl_dyn.cu
 
 struct balm_ctx {
   int N = 0, n = 0, ldg = 0, Np = 0, device = 0, prec = 0;
@@ -76,13 +75,11 @@ struct balm_ctx {
   double *syrk_part = nullptr;    // [splits][tiles][128*128]
 
   // ---- tensor path (int8 split-integer) ----
-  int slices = 6;
-  int8_t *Gq = nullptr;           // [slices][3*VBp][ldq] int8
+  int8_t *Gq = nullptr;           // [4][rows_alloc][ldg] int8 digit planes of rint(G' * sc) (3 or 4 used per batch)
   unsigned long long *colmax = nullptr;  // [ldg] bit patterns of max |G'[:,j]| of the current batch
   void *tmap = nullptr;           // CUtensorMap storage
 
   // ---- multi-GPU ----
-  NcclDyn *nccl = nullptr;
   void *comm = nullptr;
   int rank = 0, world = 1;
 
