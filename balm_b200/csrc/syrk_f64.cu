@@ -158,26 +158,40 @@ struct AsmArgs {
 };
 
 // H(i,j) = -sum_splits S(i,j) (+ D block on the diagonal); lower triangle mirrored from the upper tiles.
-__global__ void assemble_kernel(AsmArgs a) {
-  const int j = blockIdx.x * 32 + threadIdx.x;  // column (fast)
-  const int i = blockIdx.y * 8 + threadIdx.y;   // row
-  if (i >= a.n || j >= a.n) return;
-  const int r = i < j ? i : j, c = i < j ? j : i;  // upper-triangle source element
-  const int bi = r / TILE, bj = c / TILE;
-  const int t = bi * a.nb - bi * (bi - 1) / 2 + (bj - bi);
-  const size_t off = (size_t)t * (TILE * TILE) + (size_t)(r % TILE) * TILE + (c % TILE);
-  double s = 0.0;
-  for (int sp = 0; sp < a.splits; sp++) s += a.part[(size_t)sp * a.tiles * (TILE * TILE) + off];
-  double h = -s;
-  const int pi = r / 6, pj = c / 6;
-  if (a.exact_diag && r == c) h = -a.accum[(size_t)(27 + r % 6) * a.Np + pi];
-  if (pi == pj) {
-    const int rr = r % 6, cc = c % 6;  // rr <= cc
-    const int q = 6 + rr * 6 - rr * (rr - 1) / 2 + (cc - rr);
-    h += a.accum[(size_t)q * a.Np + pi];
+// One CTA per 32x32 block of the upper triangle: the partial tiles are read coalesced (column index fastest), the
+// mirrored (lower) element is written straight away (coalesced in the same index) and the upper element goes through
+// a shared-memory transpose so that its column-major store is coalesced too.
+__global__ void __launch_bounds__(1024) assemble_kernel(AsmArgs a) {
+  __shared__ double tile[32][33];
+  const int bx = blockIdx.x, by = blockIdx.y;  // block row bx, block column by (by >= bx)
+  if (by < bx) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int r = bx * 32 + ty, c = by * 32 + tx;  // upper-triangle source element (r <= c except inside diagonal blocks)
+  double h = 0.0;
+  if (r < a.n && c < a.n) {
+    const int rr = r < c ? r : c, cc = r < c ? c : r;
+    const int bi = rr / TILE, bj = cc / TILE;
+    const int t = bi * a.nb - bi * (bi - 1) / 2 + (bj - bi);
+    const size_t off = (size_t)t * (TILE * TILE) + (size_t)(rr % TILE) * TILE + (cc % TILE);
+    double s = 0.0;
+    for (int sp = 0; sp < a.splits; sp++) s += a.part[(size_t)sp * a.tiles * (TILE * TILE) + off];
+    h = -s;
+    const int pi = rr / 6, pj = cc / 6;
+    if (a.exact_diag && rr == cc) h = -a.accum[(size_t)(27 + rr % 6) * a.Np + pi];
+    if (pi == pj) {
+      const int r6 = rr % 6, c6 = cc % 6;  // r6 <= c6
+      const int q = 6 + r6 * 6 - r6 * (r6 - 1) / 2 + (c6 - r6);
+      h += a.accum[(size_t)q * a.Np + pi];
+    }
+    a.H[(size_t)r * a.n + c] = h;  // element (row c, col r): the mirrored (lower) one, coalesced in c
   }
-  a.H[(size_t)j * a.n + i] = h;
-  if (i == 0 && j < a.n) a.g[j] = a.accum[(size_t)(j % 6) * a.Np + j / 6];
+  tile[ty][tx] = h;
+  __syncthreads();
+  if (by > bx) {  // element (row r', col c') of the upper block, coalesced in r'
+    const int r2 = bx * 32 + tx, c2 = by * 32 + ty;
+    if (r2 < a.n && c2 < a.n) a.H[(size_t)c2 * a.n + r2] = tile[tx][ty];
+  }
+  if (bx == 0 && ty == 0 && c < a.n) a.g[c] = a.accum[(size_t)(c % 6) * a.Np + c / 6];
 }
 
 }  // namespace
@@ -196,7 +210,8 @@ int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch) {
 int launch_assemble(balm_ctx *c) {
   AsmArgs a{c->syrk_part, c->syrk_splits, c->syrk_tiles, c->syrk_nb, c->accum, c->N, c->Np, c->n,
             c->prec == BALM_PREC_TENSOR ? 1 : 0, c->H, c->g};
-  dim3 block(32, 8), grid((c->n + 31) / 32, (c->n + 7) / 8);
+  const int nbb = (c->n + 31) / 32;
+  dim3 block(32, 32), grid(nbb, nbb);
   assemble_kernel<<<grid, block, 0, c->stream>>>(a);
   c->launches += 1;
   CUDA_TRY(cudaGetLastError());
