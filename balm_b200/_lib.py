@@ -28,6 +28,11 @@ class Timings(C.Structure):
                 ("digit_planes", C.c_int)]
 
 
+class AssocOpts(C.Structure):
+    _fields_ = [("voxel_size", C.c_double), ("layer_limit", C.c_int), ("min_ps", C.c_int),
+                ("eigen_value_array", C.c_double * 3)]
+
+
 class BalmError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__(f"balm_b200 status {status}: {msg}")
@@ -41,7 +46,7 @@ SYMBOLS = ["balm_last_error", "balm_version", "balm_create", "balm_destroy", "ba
            "balm_set_voxels_dev", "balm_evaluate", "balm_residual", "balm_solve", "balm_damping_iter",
            "balm_default_lm_opts", "balm_comm_unique_id", "balm_comm_init", "balm_get_timings",
            "balm_reset_counters", "balm_sync", "balm_timer_begin", "balm_timer_end", "balm_device_views", "balm_synth_virtual",
-           "balm_download_voxels", "balm_num_obs"]
+           "balm_download_voxels", "balm_num_obs", "balm_default_assoc_opts", "balm_cut_voxels"]
 
 
 def lib():
@@ -76,6 +81,9 @@ def lib():
         L.balm_synth_virtual.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double,
                                          C.c_uint64, C.c_void_p, C.c_void_p]
         L.balm_download_voxels.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.balm_default_assoc_opts.argtypes = [C.POINTER(AssocOpts)]
+        L.balm_cut_voxels.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AssocOpts),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 

@@ -48,6 +48,19 @@ class Context:
         self.M = int(n_voxels)
         return gt, init
 
+    def cut_voxels(self, xyz, frame, poses12, voxel_size=2.0, layer_limit=2, min_ps=15,
+                   eigen_value_array=(1.0 / 16, 1.0 / 16, 1.0 / 9)):
+        """GPU association (cut_voxel + recut + tras_opt): raw body-frame points + poses -> registered plane voxels."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        frame = np.ascontiguousarray(frame, dtype=np.int32)
+        poses12 = np.ascontiguousarray(poses12, dtype=np.float64)
+        o = L.AssocOpts(float(voxel_size), int(layer_limit), int(min_ps), (C.c_double * 3)(*eigen_value_array))
+        M, K = C.c_int64(), C.c_int64()
+        L.check(L.lib().balm_cut_voxels(self._h, len(frame), _p(xyz), _p(frame), _p(poses12), C.byref(o), C.byref(M),
+                                        C.byref(K)))
+        self.M = M.value
+        return M.value, K.value
+
     def download_voxels(self):
         K = L.lib().balm_num_obs(self._h)
         row_ptr = np.zeros(self.M + 1, dtype=np.int64)

@@ -1,0 +1,390 @@
+// assoc.cu -- GPU association: point clouds + poses -> plane voxels (CSR of body-frame point clusters) directly in HBM.
+//
+// Restates the step that FEEDS the hot path:
+//   cut_voxel                                  /root/reference/src/benchmark/bavoxel.hpp:1170-1223
+//   OCTO_TREE_NODE::recut / judge_eigen / cut_func                     bavoxel.hpp:654-776
+//   OCTO_TREE_NODE::tras_opt -> VOX_HESS::push_voxel                   bavoxel.hpp:908-929, 30-51
+// The reference grows a pointer octree per root voxel on the CPU. Here every point gets a hierarchical 63-bit key
+//   [root x | root y | root z | octant at layer 1 | octant at layer 2]     (19+19+19+3+3 bits, roots biased by 2^18)
+// computed with the reference's own arithmetic (float32 voxel coordinate with the "-1 for negatives" rule, float
+// voxel centres, child centre = centre +- quater_length), and the tree is evaluated level by level with radix sorts
+// and segmented reductions: for each layer L the points are sorted by the key truncated to L digits (stable, frames
+// stay ascending), (node, frame) segments are reduced to body-frame clusters (what push_voxel registers) and world-frame
+// moments (what judge_eigen tests), nodes are judged planar / not planar, and a node becomes a plane voxel iff it is
+// planar, has more than min_ps points and at least two observing frames, and every ancestor was large enough and NOT
+// planar. All reductions run in a fixed order: the result is deterministic. Output order: ascending node key
+// (digit 7 = "not split at this layer"), the order tests/assoc_ref.py uses.
+#include <cub/cub.cuh>
+#include <vector>
+#include "internal.cuh"
+
+namespace {
+
+constexpr int ROOT_BITS = 19;
+constexpr long long ROOT_BIAS = 1ll << 18;
+
+struct AssocParams {
+  double voxel_size;
+  int layer_limit, min_ps;
+  double eig[3];
+};
+
+__device__ __forceinline__ long long ref_voxel_index(double w, double vs) {
+  float loc = (float)(w / vs);           // float loc_xyz[j] = pvec_tran[j] / voxel_size     (bavoxel.hpp:1180)
+  if (loc < 0) loc -= 1.0f;              // :1181
+  return (long long)loc;                 // (int64_t) cast truncates toward zero              (:1184)
+}
+
+__global__ void point_key_kernel(const float *xyz, const int *frame, const double *poses, int64_t n, AssocParams p,
+                                 unsigned long long *key, int *bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r[9], t[3];
+  load_pose(poses + 12 * frame[i], r, t);
+  const double b[3] = {(double)xyz[3 * i], (double)xyz[3 * i + 1], (double)xyz[3 * i + 2]};
+  double w[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) w[a] = r[a * 3] * b[0] + r[a * 3 + 1] * b[1] + r[a * 3 + 2] * b[2] + t[a];
+  unsigned long long k = 0;
+  int oct1 = 0, oct2 = 0;
+  const float quater = (float)(p.voxel_size / 4.0);  // ot->quater_length (:1216)
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const long long idx = ref_voxel_index(w[a], p.voxel_size);
+    if (idx < -ROOT_BIAS || idx >= ROOT_BIAS) atomicOr(bad, 1);
+    k = (k << ROOT_BITS) | (unsigned long long)((idx + ROOT_BIAS) & ((1ll << ROOT_BITS) - 1));
+    const float c0 = (float)((0.5 + (double)idx) * p.voxel_size);  // float voxel_center (:1213-1215)
+    const int b1 = w[a] > (double)c0 ? 1 : 0;                       // cut_func :711
+    const float c1 = c0 + (float)(2 * b1 - 1) * quater;             // :717-719
+    const int b2 = w[a] > (double)c1 ? 1 : 0;
+    oct1 = (oct1 << 1) | b1;
+    oct2 = (oct2 << 1) | b2;
+  }
+  key[i] = (k << 6) | (unsigned long long)(oct1 << 3) | (unsigned long long)oct2;
+}
+
+__global__ void iota_kernel(int *v, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (int)i;
+}
+__global__ void gather_frame_kernel(const int *frame, const int *idx, unsigned *out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (unsigned)frame[idx[i]];
+}
+// key of layer L: digits below L forced to 7 ("not split")
+__global__ void level_key_kernel(const unsigned long long *key, const int *idx, unsigned long long *out, int64_t n, int L) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long k = key[idx[i]];
+  if (L == 0) k |= 63ull;
+  else if (L == 1) k |= 7ull;
+  out[i] = k;
+}
+__global__ void seg_flag_kernel(const unsigned long long *keyL, const int *idx, const int *frame, int64_t n, int *flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flag[i] = (i == 0 || keyL[i] != keyL[i - 1] || frame[idx[i]] != frame[idx[i - 1]]) ? 1 : 0;
+}
+__global__ void seg_start_kernel(const int *flag, const int *scan, int64_t n, int *seg_start) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) seg_start[scan[i]] = (int)i;
+}
+
+// One thread per (node, frame) segment: body-frame cluster (PointCluster::push, tools.hpp:311-316) and world-frame
+// moments, accumulated in sorted order.
+__global__ void seg_reduce_kernel(const float *xyz, const int *frame, const double *poses, const int *idx,
+                                  const unsigned long long *keyL, const int *seg_start, int nseg, int64_t n,
+                                  double *segB, double *segW, int *seg_frame, unsigned long long *seg_key) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const int64_t a = seg_start[s], b = (s + 1 < nseg) ? seg_start[s + 1] : n;
+  const int f = frame[idx[a]];
+  double r[9], t[3];
+  load_pose(poses + 12 * f, r, t);
+  double B[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, W[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = a; i < b; i++) {
+    const int j = idx[i];
+    const double x = xyz[3 * j], y = xyz[3 * j + 1], z = xyz[3 * j + 2];
+    B[0] += x * x; B[1] += x * y; B[2] += x * z; B[3] += y * y; B[4] += y * z; B[5] += z * z;
+    B[6] += x; B[7] += y; B[8] += z; B[9] += 1.0;
+    const double wx = r[0] * x + r[1] * y + r[2] * z + t[0];
+    const double wy = r[3] * x + r[4] * y + r[5] * z + t[1];
+    const double wz = r[6] * x + r[7] * y + r[8] * z + t[2];
+    W[0] += wx * wx; W[1] += wx * wy; W[2] += wx * wz; W[3] += wy * wy; W[4] += wy * wz; W[5] += wz * wz;
+    W[6] += wx; W[7] += wy; W[8] += wz; W[9] += 1.0;
+  }
+#pragma unroll
+  for (int c = 0; c < 10; c++) { segB[(size_t)c * nseg + s] = B[c]; segW[(size_t)c * nseg + s] = W[c]; }
+  seg_frame[s] = f;
+  seg_key[s] = keyL[a];
+}
+__global__ void node_flag_kernel(const unsigned long long *seg_key, int nseg, int *flag) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nseg) flag[s] = (s == 0 || seg_key[s] != seg_key[s - 1]) ? 1 : 0;
+}
+// One thread per node: total world moments over its frames -> judge_eigen (bavoxel.hpp:654-699)
+__global__ void node_judge_kernel(const double *segW, const unsigned long long *seg_key, const int *node_start, int nnode,
+                                  int nseg, double eig_thr, unsigned long long *node_key, int *node_size,
+                                  int *node_planar, int *node_nframes) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nnode) return;
+  const int a = node_start[v], b = (v + 1 < nnode) ? node_start[v + 1] : nseg;
+  double W[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s = a; s < b; s++)
+#pragma unroll
+    for (int c = 0; c < 10; c++) W[c] += segW[(size_t)c * nseg + s];
+  const double inv = 1.0 / W[9];
+  const double c0 = W[6] * inv, c1 = W[7] * inv, c2 = W[8] * inv;
+  double lam[3], u0[3], u1[3], u2[3];
+  eig3_jacobi(W[0] * inv - c0 * c0, W[1] * inv - c0 * c1, W[2] * inv - c0 * c2, W[3] * inv - c1 * c1,
+              W[4] * inv - c1 * c2, W[5] * inv - c2 * c2, lam, u0, u1, u2);
+  node_key[v] = seg_key[a];
+  node_size[v] = (int)(W[9] + 0.5);
+  node_planar[v] = (lam[0] / lam[1] < eig_thr) ? 1 : 0;  // decision < eigen_value_array[layer]  (:665,697)
+  node_nframes[v] = b - a;
+}
+
+struct LevelTables {  // device arrays of one layer
+  int nseg = 0, nnode = 0;
+  double *segB = nullptr;          // [10][nseg] body-frame clusters
+  int *seg_frame = nullptr;
+  int *node_start = nullptr;       // [nnode] first segment
+  unsigned long long *node_key = nullptr;
+  int *node_size = nullptr, *node_planar = nullptr, *node_nframes = nullptr, *node_leaf = nullptr;
+  void release() {
+    cudaFree(segB); cudaFree(seg_frame); cudaFree(node_start); cudaFree(node_key); cudaFree(node_size);
+    cudaFree(node_planar); cudaFree(node_nframes); cudaFree(node_leaf);
+  }
+};
+
+__device__ __forceinline__ int find_key(const unsigned long long *keys, int n, unsigned long long k) {
+  int lo = 0, hi = n - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const unsigned long long v = keys[mid];
+    if (v == k) return mid;
+    if (v < k) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+// recut (bavoxel.hpp:737-776) evaluated per node: a node is reached iff every ancestor had more than min_ps points and
+// failed the planarity test; it becomes a plane voxel iff it is planar with more than min_ps points (push_state = 1)
+// and at least two frames observe it (push_voxel :37).
+__global__ void leaf_decide_kernel(int L, int nnode, const unsigned long long *key, const int *size, const int *planar,
+                                   const int *nframes, const unsigned long long *key0, const int *size0,
+                                   const int *planar0, int n0, const unsigned long long *key1, const int *size1,
+                                   const int *planar1, int n1, int min_ps, int layer_limit, int *leaf) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nnode) return;
+  bool reached = L <= layer_limit;
+  if (reached && L >= 1) {
+    const int r = find_key(key0, n0, key[v] | 63ull);
+    reached = r >= 0 && size0[r] > min_ps && !planar0[r];
+  }
+  if (reached && L >= 2) {
+    const int r = find_key(key1, n1, key[v] | 7ull);
+    reached = r >= 0 && size1[r] > min_ps && !planar1[r];
+  }
+  leaf[v] = (reached && size[v] > min_ps && planar[v] && nframes[v] >= 2) ? 1 : 0;
+}
+
+__global__ void leaf_collect_kernel(int L, int nnode, const int *leaf, const int *leaf_scan, const unsigned long long *key,
+                                    unsigned long long *out_key, int *out_ref, int base) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nnode || !leaf[v]) return;
+  const int o = base + leaf_scan[v];
+  out_key[o] = key[v];
+  out_ref[o] = (L << 28) | v;  // layer and node id
+}
+__global__ void leaf_count_kernel(const int *ref, int nleaf, const int *nf0, const int *nf1, const int *nf2, int *cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nleaf) return;
+  const int L = ref[i] >> 28, v = ref[i] & 0x0FFFFFFF;
+  cnt[i] = (L == 0 ? nf0 : (L == 1 ? nf1 : nf2))[v];
+}
+struct EmitLevel {
+  const double *segB;
+  const int *seg_frame, *node_start, *node_size;
+  int nseg;
+};
+__global__ void emit_kernel(const int *ref, const int *obs_start, int nleaf, EmitLevel e0, EmitLevel e1, EmitLevel e2,
+                            const int *cnt, double *obs, int64_t Kp, int *pose_idx, long long *row_ptr, double *coe) {
+  const int i = blockIdx.x;  // one CTA per plane voxel
+  if (i >= nleaf) return;
+  const int L = ref[i] >> 28, v = ref[i] & 0x0FFFFFFF;
+  const EmitLevel e = L == 0 ? e0 : (L == 1 ? e1 : e2);
+  const int s0 = e.node_start[v], k = cnt[i], o0 = obs_start[i];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 10; c++) obs[(size_t)c * Kp + o0 + j] = e.segB[(size_t)c * e.nseg + s0 + j];
+    pose_idx[o0 + j] = e.seg_frame[s0 + j];
+  }
+  if (threadIdx.x == 0) {
+    row_ptr[i] = o0;
+    coe[i] = (double)e.node_size[v];  // coe = sum of N over the window (bavoxel.hpp:42-44)
+    if (i == nleaf - 1) row_ptr[nleaf] = o0 + k;
+  }
+}
+
+template <typename T>
+int dalloc(T **p, size_t n) {
+  CUDA_TRY(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
+  return BALM_OK;
+}
+#define ATRY(x) do { int _s = (x); if (_s != BALM_OK) return _s; } while (0)
+
+}  // namespace
+
+// Builds the plane voxels of `ctx` from raw scans. xyz (n x 3 float32, body frame) and frame (n) are HOST arrays,
+// poses12 the initial poses. On success the voxels are registered exactly as balm_set_voxels would have done.
+int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, const double *poses12_h,
+                double voxel_size, int layer_limit, int min_ps, const double *eig3, int64_t *M_out, int64_t *K_out,
+                int (*register_csr)(balm_ctx *, int64_t, int64_t)) {
+  if (n < 1 || n >= (1ll << 31) || layer_limit < 0 || layer_limit > 2) {
+    balm_set_error("balm_cut_voxels: bad arguments (n < 2^31, layer_limit in 0..2)");
+    return BALM_ERR_INVALID;
+  }
+  cudaStream_t st = c->stream;
+  AssocParams P{voxel_size, layer_limit, min_ps, {eig3[0], eig3[1], eig3[2]}};
+  float *xyz = nullptr;
+  int *frame = nullptr, *idx = nullptr, *idx2 = nullptr, *flag = nullptr, *scan = nullptr, *seg_start = nullptr, *bad = nullptr;
+  unsigned *fkey = nullptr, *fkey2 = nullptr;
+  unsigned long long *key = nullptr, *keyL = nullptr, *keyL2 = nullptr;
+  double *poses = nullptr;
+  ATRY(dalloc(&xyz, (size_t)3 * n)); ATRY(dalloc(&frame, (size_t)n)); ATRY(dalloc(&idx, (size_t)n)); ATRY(dalloc(&idx2, (size_t)n));
+  ATRY(dalloc(&flag, (size_t)n)); ATRY(dalloc(&scan, (size_t)n)); ATRY(dalloc(&seg_start, (size_t)n)); ATRY(dalloc(&bad, 1));
+  ATRY(dalloc(&fkey, (size_t)n)); ATRY(dalloc(&fkey2, (size_t)n));
+  ATRY(dalloc(&key, (size_t)n)); ATRY(dalloc(&keyL, (size_t)n)); ATRY(dalloc(&keyL2, (size_t)n));
+  ATRY(dalloc(&poses, (size_t)12 * c->N));
+  CUDA_TRY(cudaMemcpyAsync(xyz, xyz_h, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(frame, frame_h, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(poses, poses12_h, sizeof(double) * 12 * c->N, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int), st));
+  const unsigned gb = (unsigned)((n + 255) / 256);
+  point_key_kernel<<<gb, 256, 0, st>>>(xyz, frame, poses, n, P, key, bad);
+  // stable order by frame first, so that every later stable sort keeps the frames ascending inside a node
+  iota_kernel<<<gb, 256, 0, st>>>(idx, n);
+  gather_frame_kernel<<<gb, 256, 0, st>>>(frame, idx, fkey, n);
+  size_t tmp_bytes = 0, tb2 = 0, tb3 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, fkey, fkey2, idx, idx2, (int)n, 0, 32, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, tb2, keyL, keyL2, idx, idx2, (int)n, 0, 63, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb3, flag, scan, (int)n, st);
+  tmp_bytes = std::max(tmp_bytes, std::max(tb2, tb3));
+  void *tmp = nullptr;
+  CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, fkey, fkey2, idx, idx2, (int)n, 0, 32, st);
+  int *order = idx2;   // frame-sorted point order
+  int *work = idx;     // per-level sorted order
+  c->launches += 4;
+
+  LevelTables T[3];
+  for (int L = 0; L <= layer_limit; L++) {
+    level_key_kernel<<<gb, 256, 0, st>>>(key, order, keyL, n, L);
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keyL, keyL2, order, work, (int)n, 0, 63, st);
+    seg_flag_kernel<<<gb, 256, 0, st>>>(keyL2, work, frame, n, flag);
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, scan, (int)n, st);
+    int last_flag = 0, last_scan = 0;
+    CUDA_TRY(cudaMemcpyAsync(&last_flag, flag + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&last_scan, scan + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int nseg = last_scan + last_flag;
+    seg_start_kernel<<<gb, 256, 0, st>>>(flag, scan, n, seg_start);
+    LevelTables &t = T[L];
+    t.nseg = nseg;
+    double *segW = nullptr;
+    unsigned long long *seg_key = nullptr;
+    int *nflag = nullptr, *nscan = nullptr;
+    ATRY(dalloc(&t.segB, (size_t)10 * nseg)); ATRY(dalloc(&segW, (size_t)10 * nseg)); ATRY(dalloc(&t.seg_frame, (size_t)nseg));
+    ATRY(dalloc(&seg_key, (size_t)nseg)); ATRY(dalloc(&nflag, (size_t)nseg)); ATRY(dalloc(&nscan, (size_t)nseg));
+    const unsigned gs = (unsigned)((nseg + 127) / 128);
+    seg_reduce_kernel<<<gs, 128, 0, st>>>(xyz, frame, poses, work, keyL2, seg_start, nseg, n, t.segB, segW, t.seg_frame, seg_key);
+    node_flag_kernel<<<gs, 128, 0, st>>>(seg_key, nseg, nflag);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, nflag, nscan, nseg, st);
+    if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nflag, nscan, nseg, st);
+    CUDA_TRY(cudaMemcpyAsync(&last_flag, nflag + nseg - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&last_scan, nscan + nseg - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    t.nnode = last_scan + last_flag;
+    ATRY(dalloc(&t.node_start, (size_t)t.nnode)); ATRY(dalloc(&t.node_key, (size_t)t.nnode));
+    ATRY(dalloc(&t.node_size, (size_t)t.nnode)); ATRY(dalloc(&t.node_planar, (size_t)t.nnode));
+    ATRY(dalloc(&t.node_nframes, (size_t)t.nnode)); ATRY(dalloc(&t.node_leaf, (size_t)t.nnode));
+    seg_start_kernel<<<gs, 128, 0, st>>>(nflag, nscan, nseg, t.node_start);
+    node_judge_kernel<<<(unsigned)((t.nnode + 127) / 128), 128, 0, st>>>(segW, seg_key, t.node_start, t.nnode, nseg, P.eig[L],
+                                                                        t.node_key, t.node_size, t.node_planar, t.node_nframes);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(segW); cudaFree(seg_key); cudaFree(nflag); cudaFree(nscan);
+    c->launches += 9;
+  }
+  int h_bad = 0;
+  CUDA_TRY(cudaMemcpy(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h_bad) { balm_set_error("balm_cut_voxels: a point lies outside the +-2^18 root-voxel range"); return BALM_ERR_INVALID; }
+
+  // ---- leaves of every layer, merged in key order ----
+  int nleaf_L[3] = {0, 0, 0};
+  int *lscan[3] = {nullptr, nullptr, nullptr};
+  for (int L = 0; L <= layer_limit; L++) {
+    LevelTables &t = T[L];
+    leaf_decide_kernel<<<(unsigned)((t.nnode + 127) / 128), 128, 0, st>>>(
+        L, t.nnode, t.node_key, t.node_size, t.node_planar, t.node_nframes, T[0].node_key, T[0].node_size, T[0].node_planar,
+        T[0].nnode, T[1].node_key, T[1].node_size, T[1].node_planar, T[1].nnode, min_ps, layer_limit, t.node_leaf);
+    ATRY(dalloc(&lscan[L], (size_t)t.nnode));
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, t.node_leaf, lscan[L], t.nnode, st);
+    if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, t.node_leaf, lscan[L], t.nnode, st);
+    int a = 0, b = 0;
+    CUDA_TRY(cudaMemcpyAsync(&a, t.node_leaf + t.nnode - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&b, lscan[L] + t.nnode - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    nleaf_L[L] = a + b;
+  }
+  const int nleaf = nleaf_L[0] + nleaf_L[1] + nleaf_L[2];
+  if (nleaf < 1) { balm_set_error("balm_cut_voxels: no plane voxels found"); return BALM_ERR_INVALID; }
+  unsigned long long *lkey = nullptr, *lkey2 = nullptr;
+  int *lref = nullptr, *lref2 = nullptr, *lcnt = nullptr, *lobs = nullptr;
+  ATRY(dalloc(&lkey, (size_t)nleaf)); ATRY(dalloc(&lkey2, (size_t)nleaf)); ATRY(dalloc(&lref, (size_t)nleaf));
+  ATRY(dalloc(&lref2, (size_t)nleaf)); ATRY(dalloc(&lcnt, (size_t)nleaf)); ATRY(dalloc(&lobs, (size_t)nleaf));
+  int base = 0;
+  for (int L = 0; L <= layer_limit; L++) {
+    leaf_collect_kernel<<<(unsigned)((T[L].nnode + 127) / 128), 128, 0, st>>>(L, T[L].nnode, T[L].node_leaf, lscan[L],
+                                                                             T[L].node_key, lkey, lref, base);
+    base += nleaf_L[L];
+  }
+  {
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, lkey, lkey2, lref, lref2, nleaf, 0, 63, st);
+    if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lkey, lkey2, lref, lref2, nleaf, 0, 63, st);
+  }
+  leaf_count_kernel<<<(unsigned)((nleaf + 127) / 128), 128, 0, st>>>(lref2, nleaf, T[0].node_nframes, T[1].node_nframes,
+                                                                    T[2].node_nframes, lcnt);
+  {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, lcnt, lobs, nleaf, st);
+    if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, lcnt, lobs, nleaf, st);
+  }
+  int a = 0, b = 0;
+  CUDA_TRY(cudaMemcpyAsync(&a, lcnt + nleaf - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&b, lobs + nleaf - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const int64_t K = (int64_t)a + b;
+  // ---- register: allocate the problem arrays of the context and emit straight into them ----
+  ATRY(register_csr(c, nleaf, K));
+  EmitLevel e[3];
+  for (int L = 0; L < 3; L++) e[L] = EmitLevel{T[L].segB, T[L].seg_frame, T[L].node_start, T[L].node_size, T[L].nseg};
+  emit_kernel<<<nleaf, 64, 0, st>>>(lref2, lobs, nleaf, e[0], e[1], e[2], lcnt, c->obs, c->Kp, c->pose_idx, c->row_ptr, c->coe);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 12;
+  for (int L = 0; L < 3; L++) { T[L].release(); cudaFree(lscan[L]); }
+  cudaFree(xyz); cudaFree(frame); cudaFree(idx); cudaFree(idx2); cudaFree(flag); cudaFree(scan); cudaFree(seg_start);
+  cudaFree(bad); cudaFree(fkey); cudaFree(fkey2); cudaFree(key); cudaFree(keyL); cudaFree(keyL2); cudaFree(poses);
+  cudaFree(tmp); cudaFree(lkey); cudaFree(lkey2); cudaFree(lref); cudaFree(lref2); cudaFree(lcnt); cudaFree(lobs);
+  *M_out = nleaf;
+  *K_out = K;
+  return BALM_OK;
+}

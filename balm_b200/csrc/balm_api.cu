@@ -351,6 +351,33 @@ extern "C" int balm_set_voxels_dev(balm_ctx *c, int64_t M, const int64_t *row_pt
 
 extern "C" int64_t balm_num_obs(balm_ctx *c) { return c ? c->K : 0; }
 
+// ---------------- association on the GPU (assoc.cu) ----------------
+int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, const double *poses12_h,
+                double voxel_size, int layer_limit, int min_ps, const double *eig3, int64_t *M_out, int64_t *K_out,
+                int (*register_csr)(balm_ctx *, int64_t, int64_t));
+
+static int assoc_register(balm_ctx *c, int64_t M, int64_t K) { return alloc_problem_arrays(c, M, K, false); }
+
+extern "C" void balm_default_assoc_opts(balm_assoc_opts *o) {
+  o->voxel_size = 1.0; o->layer_limit = 2; o->min_ps = 15;
+  o->eigen_value_array[0] = o->eigen_value_array[1] = o->eigen_value_array[2] = 1.0 / 16;
+}
+
+extern "C" int balm_cut_voxels(balm_ctx *c, int64_t n_points, const float *xyz, const int32_t *frame,
+                               const double *poses12, const balm_assoc_opts *opts, int64_t *n_voxels_out,
+                               int64_t *n_obs_out) {
+  if (!c || !xyz || !frame || !poses12) { balm_set_error("balm_cut_voxels: bad arguments"); return BALM_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  balm_assoc_opts o;
+  if (opts) o = *opts; else balm_default_assoc_opts(&o);
+  int64_t M = 0, K = 0;
+  TRY(assoc_build(c, n_points, xyz, frame, poses12, o.voxel_size, o.layer_limit, o.min_ps, o.eigen_value_array, &M, &K,
+                  assoc_register));
+  if (n_voxels_out) *n_voxels_out = M;
+  if (n_obs_out) *n_obs_out = K;
+  return finish_registration(c);
+}
+
 extern "C" int balm_download_voxels(balm_ctx *c, int64_t *row_ptr, int32_t *pose_idx, double *obs10, double *coe) {
   if (!c || !c->obs) { balm_set_error("balm_download_voxels: no voxels registered"); return BALM_ERR_INVALID; }
   CUDA_TRY(cudaSetDevice(c->device));

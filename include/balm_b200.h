@@ -110,6 +110,22 @@ int balm_damping_iter(balm_ctx *ctx, double *poses12, const balm_lm_opts *opts, 
                       double *poses_per_iter);
 void balm_default_lm_opts(balm_lm_opts *opts);
 
+/* Association on the GPU: raw scans + initial poses -> plane voxels, registered in the
+ * ctx exactly as balm_set_voxels would. Replaces the loop  cut_voxel(surf_map, *pl_fulls[i], x_buf[i], i)  over all scans
+ * followed by  recut(win_size); tras_opt(voxhess, win_size)  over all root voxels
+ * (benchmark_realworld.cpp:187-200 -> bavoxel.hpp:1170-1223, 737-776, 908-929, 30-51).
+ * xyz: n_points x 3 float32 in the BODY frame (the PCD floats), frame: n_points pose indices, poses12: N x 12.
+ * opts may be NULL (reference constants: voxel_size 1, layer_limit 2, min_ps 15, eigen ratios 1/16). */
+typedef struct {
+  double voxel_size;          /* bavoxel.hpp:15; benchmark_realworld.launch sets 2 */
+  int layer_limit;            /* bavoxel.hpp:8  (0..2) */
+  int min_ps;                 /* bavoxel.hpp:12 */
+  double eigen_value_array[3];/* bavoxel.hpp:11; benchmark_realworld.cpp:183-185 sets {1/16, 1/16, 1/9} */
+} balm_assoc_opts;
+void balm_default_assoc_opts(balm_assoc_opts *opts);
+int balm_cut_voxels(balm_ctx *ctx, int64_t n_points, const float *xyz, const int32_t *frame, const double *poses12,
+                    const balm_assoc_opts *opts, int64_t *n_voxels_out, int64_t *n_obs_out);
+
 /* Multi-GPU: voxels are sharded across ranks by the caller (each rank registers its own shard); the library
  * all-reduces [H | g | r] with NCCL after every evaluation and the scalar after every residual pass.
  * unique_id: 128 bytes from balm_comm_unique_id() on rank 0, broadcast by the caller (torch.distributed, MPI). */

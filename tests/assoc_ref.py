@@ -1,0 +1,124 @@
+"""numpy restatement of the reference's association step -- the oracle of the GPU association (balm_cut_voxels).
+
+  cut_voxel                                     src/benchmark/bavoxel.hpp:1170-1223
+      world point = R p + t; float32 voxel coordinate loc = world / voxel_size, "-1 for negatives", truncation to
+      int64 (:1178-1184); root centre (0.5 + idx) * voxel_size stored as float (:1213-1215), quater_length = size/4
+  OCTO_TREE_NODE::recut / judge_eigen / cut_func bavoxel.hpp:654-776
+      a node with <= min_ps points is dropped; planar (lambda0/lambda1 < eigen_value_array[layer], covariance of ALL the
+      node's world points) -> plane leaf; otherwise split into octants around the float centre (child centre =
+      centre +- quater, quater/2) until layer_limit
+  tras_opt -> VOX_HESS::push_voxel              bavoxel.hpp:908-929, 30-51
+      leaves with >= min_ps points and >= 2 observing frames become plane voxels; per-frame clusters are the moments
+      of the BODY-frame points (sig_orig), coe = total point count
+Returns CSR arrays ordered by the 63-bit node key (root x,y,z biased by 2^18 in 19 bits each, then the two octant
+digits, 7 = "not split"), which is also the order the GPU implementation emits.
+"""
+import numpy as np
+
+DEFAULTS = dict(voxel_size=2.0, layer_limit=2, min_ps=15, layer_size=(30, 30, 30, 30),
+                eigen_value_array=(1.0 / 16, 1.0 / 16, 1.0 / 9, 1.0 / 16))
+
+
+def root_index(world, voxel_size):
+    loc = (world / voxel_size).astype(np.float32)
+    loc = np.where(loc < 0, loc - np.float32(1.0), loc)
+    return np.trunc(loc).astype(np.int64)
+
+
+def node_key(root, o1, o2):
+    b = 1 << 18
+    return (((int(root[0]) + b) << 44) | ((int(root[1]) + b) << 25) | ((int(root[2]) + b) << 6) | (o1 << 3) | o2)
+
+
+def cut_voxels(points_body, frames, poses, **kw):
+    """points_body: n x 3 float64 (already rounded to the float32 the PCD stores), frames: n int, poses: list of (R, p)."""
+    o = dict(DEFAULTS)
+    o.update(kw)
+    vs, lim, min_ps = o["voxel_size"], o["layer_limit"], o["min_ps"]
+    R = np.stack([r for r, _ in poses])
+    t = np.stack([p for _, p in poses])
+    world = np.einsum("nij,nj->ni", R[frames], points_body) + t[frames]
+    key = root_index(world, vs)
+    order = np.lexsort((frames, key[:, 2], key[:, 1], key[:, 0]))
+    key, pb, pw, fr = key[order], points_body[order], world[order], frames[order]
+    change = np.any(key[1:] != key[:-1], axis=1)
+    starts = np.concatenate([[0], np.nonzero(change)[0] + 1, [len(key)]])
+    leaves = []
+
+    def recut(pb_, pw_, fr_, center, quater, layer, root, path):
+        n = len(pb_)
+        if n <= min_ps:
+            return
+        c = pw_.sum(0) / n
+        cov = pw_.T @ pw_ / n - np.outer(c, c)
+        lam = np.linalg.eigvalsh(cov)
+        if lam[0] / lam[1] < o["eigen_value_array"][layer]:
+            leaves.append((node_key(root, path[0], path[1]), pb_, fr_))
+            return
+        if layer == lim:
+            return
+        octant = pw_ > center[None, :]
+        leaf = 4 * octant[:, 0] + 2 * octant[:, 1] + octant[:, 2]
+        for lf in range(8):
+            m = leaf == lf
+            if not m.any():
+                continue
+            xyz = np.array([(lf >> 2) & 1, (lf >> 1) & 1, lf & 1])
+            cc = (center.astype(np.float32) + (2 * xyz - 1).astype(np.float32) * np.float32(quater)).astype(np.float64)
+            p2 = (lf, 7) if layer == 0 else (path[0], lf)
+            recut(pb_[m], pw_[m], fr_[m], cc, quater / 2, layer + 1, root, p2)
+
+    for a, b in zip(starts[:-1], starts[1:]):
+        center = ((0.5 + key[a]) * vs).astype(np.float32).astype(np.float64)
+        recut(pb[a:b], pw[a:b], fr[a:b], center, vs / 4.0, 0, key[a], (7, 7))
+    leaves.sort(key=lambda x: x[0])
+    row_ptr, pose_idx, obs, coe, keys = [0], [], [], [], []
+    for k, q, f in leaves:
+        fs = np.unique(f)
+        if len(q) < min_ps or len(fs) < 2:
+            continue
+        for ff in fs:
+            x = q[f == ff]
+            P = x.T @ x
+            v = x.sum(0)
+            obs.append([P[0, 0], P[0, 1], P[0, 2], P[1, 1], P[1, 2], P[2, 2], v[0], v[1], v[2], float(len(x))])
+            pose_idx.append(int(ff))
+        row_ptr.append(len(pose_idx))
+        coe.append(float(len(q)))
+        keys.append(k)
+    return (np.array(row_ptr, dtype=np.int64), np.array(pose_idx, dtype=np.int32), np.array(obs, dtype=np.float64),
+            np.array(coe, dtype=np.float64), np.array(keys, dtype=np.int64))
+
+
+def synthetic_scans(n_poses=12, pts_per_scan=6000, seed=5, room=6.0):
+    """Lidar-like scans of a box room with a few interior planes and clutter, seen from a short trajectory with noisy
+    initial poses -- exercises planar roots, split roots (wall/floor corners) and non-planar clutter."""
+    import scenes
+    rng = np.random.default_rng(seed)
+    Rs = [scenes.exp_so3(np.array([0.02 * i, -0.015 * i, 0.05 * i])) for i in range(n_poses)]
+    ps = [np.array([0.15 * i, 0.1 * np.sin(0.5 * i), 0.02 * i]) for i in range(n_poses)]
+    pts, frs = [], []
+    for i in range(n_poses):
+        n = pts_per_scan
+        face = rng.integers(0, 8, n)
+        u, v = rng.uniform(-room, room, n), rng.uniform(-room, room, n)
+        w = np.zeros((n, 3))
+        for fidx in range(6):  # the six room faces
+            m = face == fidx
+            ax, sgn = fidx // 2, (1 if fidx % 2 else -1)
+            q = np.zeros((m.sum(), 3))
+            q[:, ax] = sgn * room
+            q[:, (ax + 1) % 3] = u[m]
+            q[:, (ax + 2) % 3] = v[m]
+            w[m] = q
+        m = face == 6  # a slanted interior plane
+        w[m] = np.stack([u[m] * 0.5, v[m] * 0.5, 0.3 * u[m] + 0.2 * v[m] - 1.0], axis=1)
+        m = face == 7  # clutter (non-planar blobs)
+        w[m] = rng.normal(0, 0.6, (m.sum(), 3)) + rng.choice([-3.0, 0.0, 3.0], (m.sum(), 3))
+        w += rng.normal(0, 0.01, w.shape)
+        body = (w - ps[i]) @ Rs[i]  # R^T (x - p)
+        pts.append(body.astype(np.float32).astype(np.float64))
+        frs.append(np.full(n, i, dtype=np.int32))
+    noisy = [(Rs[i] @ scenes.exp_so3(rng.normal(0, 0.003, 3)), ps[i] + rng.normal(0, 0.01, 3)) for i in range(n_poses)]
+    noisy[0] = (Rs[0], ps[0])
+    return np.concatenate(pts), np.concatenate(frs), noisy
