@@ -15,6 +15,7 @@
 // planar. All reductions run in a fixed order: the result is deterministic. Output order: ascending node key
 // (digit 7 = "not split at this layer"), the order tests/assoc_ref.py uses.
 #include <cub/cub.cuh>
+#include <algorithm>
 #include <vector>
 #include "internal.cuh"
 
@@ -35,12 +36,14 @@ __device__ __forceinline__ long long ref_voxel_index(double w, double vs) {
   return (long long)loc;                 // (int64_t) cast truncates toward zero              (:1184)
 }
 
-__global__ void point_key_kernel(const float *xyz, const int *frame, const double *poses, int64_t n, AssocParams p,
-                                 unsigned long long *key, int *bad) {
+__global__ void point_key_kernel(const float *xyz, const int *frame, const double *poses, int n_poses, int64_t n,
+                                 AssocParams p, unsigned long long *key, int *bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  int f = frame[i];
+  if (f < 0 || f >= n_poses) { atomicOr(bad, 2); f = 0; }
   double r[9], t[3];
-  load_pose(poses + 12 * frame[i], r, t);
+  load_pose(poses + 12 * f, r, t);
   const double b[3] = {(double)xyz[3 * i], (double)xyz[3 * i + 1], (double)xyz[3 * i + 2]};
   double w[3];
 #pragma unroll
@@ -262,7 +265,7 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   CUDA_TRY(cudaMemcpyAsync(poses, poses12_h, sizeof(double) * 12 * c->N, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int), st));
   const unsigned gb = (unsigned)((n + 255) / 256);
-  point_key_kernel<<<gb, 256, 0, st>>>(xyz, frame, poses, n, P, key, bad);
+  point_key_kernel<<<gb, 256, 0, st>>>(xyz, frame, poses, c->N, n, P, key, bad);
   // stable order by frame first, so that every later stable sort keeps the frames ascending inside a node
   iota_kernel<<<gb, 256, 0, st>>>(idx, n);
   gather_frame_kernel<<<gb, 256, 0, st>>>(frame, idx, fkey, n);
@@ -273,7 +276,7 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   tmp_bytes = std::max(tmp_bytes, std::max(tb2, tb3));
   void *tmp = nullptr;
   CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
-  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, fkey, fkey2, idx, idx2, (int)n, 0, 32, st);
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, fkey, fkey2, idx, idx2, (int)n, 0, 32, st));
   int *order = idx2;   // frame-sorted point order
   int *work = idx;     // per-level sorted order
   c->launches += 4;
@@ -281,9 +284,9 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   LevelTables T[3];
   for (int L = 0; L <= layer_limit; L++) {
     level_key_kernel<<<gb, 256, 0, st>>>(key, order, keyL, n, L);
-    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keyL, keyL2, order, work, (int)n, 0, 63, st);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keyL, keyL2, order, work, (int)n, 0, 63, st));
     seg_flag_kernel<<<gb, 256, 0, st>>>(keyL2, work, frame, n, flag);
-    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, scan, (int)n, st);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, scan, (int)n, st));
     int last_flag = 0, last_scan = 0;
     CUDA_TRY(cudaMemcpyAsync(&last_flag, flag + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&last_scan, scan + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -303,7 +306,7 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, nflag, nscan, nseg, st);
     if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
-    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nflag, nscan, nseg, st);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nflag, nscan, nseg, st));
     CUDA_TRY(cudaMemcpyAsync(&last_flag, nflag + nseg - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&last_scan, nscan + nseg - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -320,7 +323,11 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   }
   int h_bad = 0;
   CUDA_TRY(cudaMemcpy(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost));
-  if (h_bad) { balm_set_error("balm_cut_voxels: a point lies outside the +-2^18 root-voxel range"); return BALM_ERR_INVALID; }
+  if (h_bad) {
+    balm_set_error(h_bad & 2 ? "balm_cut_voxels: frame index outside [0, n_poses)"
+                             : "balm_cut_voxels: a point lies outside the +-2^18 root-voxel range");
+    return BALM_ERR_INVALID;
+  }
 
   // ---- leaves of every layer, merged in key order ----
   int nleaf_L[3] = {0, 0, 0};
@@ -334,7 +341,7 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, t.node_leaf, lscan[L], t.nnode, st);
     if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
-    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, t.node_leaf, lscan[L], t.nnode, st);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, t.node_leaf, lscan[L], t.nnode, st));
     int a = 0, b = 0;
     CUDA_TRY(cudaMemcpyAsync(&a, t.node_leaf + t.nnode - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&b, lscan[L] + t.nnode - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -357,7 +364,7 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, lkey, lkey2, lref, lref2, nleaf, 0, 63, st);
     if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
-    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lkey, lkey2, lref, lref2, nleaf, 0, 63, st);
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lkey, lkey2, lref, lref2, nleaf, 0, 63, st));
   }
   leaf_count_kernel<<<(unsigned)((nleaf + 127) / 128), 128, 0, st>>>(lref2, nleaf, T[0].node_nframes, T[1].node_nframes,
                                                                     T[2].node_nframes, lcnt);
@@ -365,7 +372,7 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, lcnt, lobs, nleaf, st);
     if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
-    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, lcnt, lobs, nleaf, st);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, lcnt, lobs, nleaf, st));
   }
   int a = 0, b = 0;
   CUDA_TRY(cudaMemcpyAsync(&a, lcnt + nleaf - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
