@@ -25,7 +25,8 @@ class Timings(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("ms_stats", "ms_obs", "ms_slice", "ms_syrk", "ms_assemble",
                                          "ms_allreduce", "ms_solve", "ms_residual", "ms_update")] + \
                [("launches", C.c_int), ("n_eval", C.c_int), ("n_solve", C.c_int), ("n_residual", C.c_int),
-                ("digit_planes", C.c_int)]
+                ("digit_planes", C.c_int), ("single_sweeps", C.c_int), ("redone_sweeps", C.c_int),
+                ("n_stats", C.c_int)]
 
 
 class AssocOpts(C.Structure):

@@ -62,8 +62,8 @@ static void free_problem(balm_ctx *c) {
   cudaFree(c->csc_ptr); cudaFree(c->csc_obs); cudaFree(c->csc_vox);
   c->obs = nullptr; c->pose_idx = nullptr; c->row_ptr = nullptr; c->coe = nullptr; c->fix = nullptr;
   c->csc_ptr = c->csc_obs = c->csc_vox = nullptr;
-  cudaFree(c->stats); cudaFree(c->G); cudaFree(c->obs_part); cudaFree(c->syrk_part);
-  c->stats = c->G = c->obs_part = c->syrk_part = nullptr;
+  cudaFree(c->stats); cudaFree(c->stats_trial); cudaFree(c->G); cudaFree(c->obs_part); cudaFree(c->syrk_part);
+  c->stats = c->stats_trial = c->G = c->obs_part = c->syrk_part = nullptr;
   tensor_syrk_free(c);
   c->M = c->K = c->Kp = 0;
 }
@@ -93,6 +93,7 @@ static int alloc_workspaces(balm_ctx *c) {
   }
   c->VB = vb;
   TRY(dev_alloc(&c->stats, (size_t)vb * BALM_STATS_STRIDE));
+  if (vb == c->M && !getenv("BALM_NO_STATS_CACHE")) TRY(dev_alloc(&c->stats_trial, (size_t)vb * BALM_STATS_STRIDE));
   if (c->prec == BALM_PREC_FP64) {  // the tensor path writes int8 digit planes directly and never stores fp64 G'
     TRY(dev_alloc(&c->G, (size_t)3 * vb * c->ldg));
     CUDA_TRY(cudaMemsetAsync(c->G, 0, sizeof(double) * (size_t)3 * vb * c->ldg, c->stream));  // zero the column padding
@@ -431,7 +432,10 @@ static int allreduce_sum(balm_ctx *c, double *buf, size_t count) {
 }
 
 // H, g, r of voxels [head,end) at device poses `poses`; result in c->H | c->g | c->scal[0] (all-reduced).
-static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t end, bool include_fix) {
+// stats_cached: c->stats already holds the per-voxel eigen data of exactly these poses (left there by the residual
+// pass of an accepted LM step, or by the evaluation before a rejected one) and c->scal[4] this rank's residual.
+static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t end, bool include_fix,
+                        bool stats_cached = false) {
   if (!c->obs) { balm_set_error("no voxels registered"); return BALM_ERR_INVALID; }
   if (head < 0 || end > c->M || head > end) { balm_set_error("evaluate: bad voxel range"); return BALM_ERR_INVALID; }
   double *r_dev = c->g + c->n;  // contiguous with H and g -> one all-reduce
@@ -446,7 +450,8 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
   for (int64_t v0 = head; v0 < end; v0 += c->VB) {
     const int64_t v1 = std::min(end, v0 + c->VB);
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    TRY(launch_voxel_stats(c, poses, v0, v1, true, include_fix, r_dev));
+    if (stats_cached) CUDA_TRY(cudaMemcpyAsync(r_dev, c->scal + 4, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    else TRY(launch_voxel_stats(c, poses, v0, v1, c->stats, include_fix, r_dev));
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     if (c->prec == BALM_PREC_TENSOR) {
       TRY(tensor_obs_and_syrk(c, poses, v0, v1, first));  // records ev[2] between the sweeps and the SYRK
@@ -457,12 +462,14 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     CUDA_TRY(cudaEventSynchronize(c->ev[3]));
-    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->tm.ms_stats += ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    if (!stats_cached) { c->tm.ms_stats += ms; if (first) c->tm.n_stats += 1; }
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->tm.ms_obs += ms;
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->tm.ms_syrk += ms;
     if (c->prec == BALM_PREC_TENSOR) TRY(tensor_syrk_check(c));
     first = false;
   }
+  CUDA_TRY(cudaMemcpyAsync(c->scal + 4, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // local, pre all-reduce
   CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
   TRY(launch_assemble(c));
   CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
@@ -476,12 +483,13 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
   return BALM_OK;
 }
 
-static int residual_dev(balm_ctx *c, const double *poses, double *host_out) {
+static int residual_dev(balm_ctx *c, const double *poses, double *host_out, bool keep_stats = false) {
   if (!c->obs) { balm_set_error("no voxels registered"); return BALM_ERR_INVALID; }
   double *r_dev = c->scal + 2;
   CUDA_TRY(cudaEventRecord(c->ev[7], c->stream));
   CUDA_TRY(cudaMemsetAsync(r_dev, 0, sizeof(double), c->stream));
-  TRY(launch_voxel_stats(c, poses, 0, c->M, false, true, r_dev));
+  TRY(launch_voxel_stats(c, poses, 0, c->M, keep_stats ? c->stats_trial : nullptr, true, r_dev));
+  CUDA_TRY(cudaMemcpyAsync(c->scal + 3, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // local, pre all-reduce
   TRY(allreduce_sum(c, r_dev, 1));
   CUDA_TRY(cudaEventRecord(c->ev[8], c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->h_scal + 2, r_dev, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -569,9 +577,14 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
   CUDA_TRY(cudaMemcpyAsync(c->poses, poses12, pbytes, cudaMemcpyHostToDevice, c->stream));
   double u = o->u0, v = o->v0, r1 = 0, r2 = 0;
   bool calc_hess = true;
+  // The residual pass at the trial poses computes the same per-voxel eigen data the next evaluation starts with:
+  // when the step is accepted they are handed over (same kernel, same inputs -> identical values). Needs the whole
+  // problem in one batch and the same treatment of the fix cluster in both passes.
+  const bool hand_over = c->stats_trial != nullptr && (c->fix == nullptr || o->hess_includes_fix != 0);
+  bool stats_cached = false;
   for (int it = 0; it < o->max_iter; it++) {
     if (calc_hess) {
-      TRY(evaluate_dev(c, c->poses, 0, c->M, o->hess_includes_fix != 0));
+      TRY(evaluate_dev(c, c->poses, 0, c->M, o->hess_includes_fix != 0, stats_cached));
       CUDA_TRY(cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       CUDA_TRY(cudaStreamSynchronize(c->stream));
       r1 = c->h_scal[0];
@@ -580,7 +593,7 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
     int not_pd = 0;
     TRY(solve_dev(c, u, &q1, &not_pd));
     TRY(launch_pose_update(c, c->poses, c->dx, c->poses_trial));
-    TRY(residual_dev(c, c->poses_trial, &r2));
+    TRY(residual_dev(c, c->poses_trial, &r2, hand_over));
     double q = r1 - r2;
     if (not_pd || !std::isfinite(r2)) q = -1.0;  // unusable step -> rejected, u *= v
     if (o->verbose)  // the reference's trace line (bavoxel.hpp:1132)
@@ -588,6 +601,11 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
     balm_trace t{r1, r2, u, v, q, q1, 0, calc_hess ? 1 : 0, not_pd};
     if (q > 0) {  // bavoxel.hpp:1134-1143
       std::swap(c->poses, c->poses_trial);
+      if (hand_over) {
+        std::swap(c->stats, c->stats_trial);
+        CUDA_TRY(cudaMemcpyAsync(c->scal + 4, c->scal + 3, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      }
+      stats_cached = hand_over;
       const double rho = q / q1;
       v = 2;
       const double f = 1 - pow(2 * rho - 1, 3);
@@ -598,6 +616,7 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
       u = u * v;
       v = 2 * v;
       calc_hess = o->force_hess != 0;
+      stats_cached = c->stats_trial != nullptr;  // c->stats still describes c->poses (single batch)
     }
     if (trace) trace[it] = t;
     if (poses_per_iter)

@@ -129,24 +129,31 @@ struct ObsArgs {
   int8_t *Gq;           // [S][rows_alloc][ldg]
   int64_t plane_stride;
   const int *S_dev;     // digit-plane count chosen on the device by tc_scale_kernel
+  const int *skip;      // OBS_INT8: the speculative single sweep was accepted -> nothing to do
   // csc
   const int *csc_ptr, *csc_obs, *csc_vox;
 };
 
 // One lane = one pose; a warp covers 32 consecutive poses and walks a chunk of voxels, so the observation
 // loads of a dense scene (slot j == pose j) are coalesced and the 27 accumulators stay in registers.
-enum { OBS_FP64 = 0, OBS_MAXONLY = 1, OBS_INT8 = 2 };
+enum { OBS_FP64 = 0, OBS_MAXONLY = 1, OBS_INT8 = 2, OBS_FUSED = 3 };
 // MODE: OBS_FP64    writes fp64 G' + gradient / diagonal blocks                          [fp64 SYRK path]
 //       OBS_MAXONLY first sweep of the tensor path: column maxima of G' (-> power-of-two column scales) and the
 //                   gradient / diagonal-block accumulators (kept here so that the second sweep is lean)
 //       OBS_INT8    second sweep: writes the balanced base-256 digit planes of rint(G' * sc) directly, so the
 //                   tensor path never materialises G' in fp64
+//       OBS_FUSED   both sweeps in one, with the column scales of the PREVIOUS evaluation of the same voxels (an LM
+//                   step moves the column maxima by far less than the factor 2 of headroom a balanced top digit
+//                   has); tc_scale_kernel checks the new maxima against the scales used and, if a column overflowed
+//                   or lost precision, re-arms the OBS_INT8 sweep (which otherwise returns at once)
 template <bool DENSE, int MODE>
 __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile = blockIdx.y * 4 + warp;
   const int i = tile * 32 + lane;
   if (tile * 32 >= a.N) return;
+  if (MODE == OBS_INT8 && a.skip && *a.skip) return;
+  constexpr bool EMIT = (MODE == OBS_INT8 || MODE == OBS_FUSED);
   const bool active = i < a.N;
   double r[9], p[3];
   if (active) load_pose(a.poses + 12 * i, r, p);
@@ -155,8 +162,8 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
   for (int q = 0; q < BALM_ACC; q++) acc[q] = 0.0;
   double cmax[6] = {0, 0, 0, 0, 0, 0};
   double scl[6] = {0, 0, 0, 0, 0, 0};
-  const int S = (MODE == OBS_INT8) ? *a.S_dev : 0;
-  if (MODE == OBS_INT8 && active) {
+  const int S = EMIT ? *a.S_dev : 0;
+  if (EMIT && active) {
 #pragma unroll
     for (int q = 0; q < 6; q++) scl[q] = __ldg(a.sc + 6 * i + q);
   }
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
           for (int h = 0; h < 3; h++) qd[h] = make_double2(gv[rr][2 * h], gv[rr][2 * h + 1]);
         }
       }
-      if (MODE == OBS_INT8) {
+      if (EMIT) {
         // |G' * sc| < 2^30, so X fits an int32 and ALL its balanced base-256 digits d_k in [-128,127] fall out of
         // two integer ops: the unsigned bytes of X + 0x80808080 are d_k + 128, and xor 0x80 turns them into int8.
 #pragma unroll
@@ -355,8 +362,9 @@ __global__ void obs_reduce_kernel(const double *part, int chunks, int total, dou
 
 }  // namespace
 
-int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool store_stats, bool use_fix,
+int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, double *stats_out, bool use_fix,
                        double *residual_out_dev) {
+  const bool store_stats = stats_out != nullptr;
   // residual_out_dev: accumulated (+=) when it is not the first batch -> caller zeroes it first
   const int64_t nv = v1 - v0;
   if (nv <= 0) return BALM_OK;
@@ -364,7 +372,7 @@ int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1,
   const int max_blocks = c->res_blocks / STATS_WARPS;
   int blocks = (int)(want < (int64_t)max_blocks ? want : max_blocks);
   StatsArgs a{c->obs, c->Kp, c->pose_idx, c->row_ptr, c->coe, use_fix ? c->fix : nullptr, c->M, poses, c->N, v0, v1,
-              store_stats ? c->stats : nullptr, c->res_part};
+              stats_out, c->res_part};
   const int psmem = 12 * c->N * (int)sizeof(double);
   const bool in_smem = psmem <= 64 * 1024;  // up to 682 poses; larger windows read the table through L1
   if (in_smem) {
@@ -444,29 +452,41 @@ int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, 
   return BALM_OK;
 }
 
-// tensor path, sweep 2: int8 digit planes written directly.
+// tensor path, sweep 2: int8 digit planes written directly. `fused`: the single speculative sweep (column maxima,
+// accumulators AND digit planes with the previous evaluation's scales); `skip`: device flag that disarms sweep 2.
 int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch, const double *sc,
-                    int8_t *Gq, int64_t plane_stride, const int *S_dev, int S_alloc, int64_t rows_padded) {
+                    int8_t *Gq, int64_t plane_stride, const int *S_dev, int S_alloc, int64_t rows_padded, bool fused,
+                    const int *skip) {
   const int64_t nv = v1 - v0;
   if (nv <= 0) return BALM_OK;
   ObsArgs a;
   obs_fill(c, a, poses, v0, v1);
-  a.sc = sc; a.Gq = Gq; a.plane_stride = plane_stride; a.S_dev = S_dev;
+  a.sc = sc; a.Gq = Gq; a.plane_stride = plane_stride; a.S_dev = S_dev; a.skip = skip;
   const int S = S_alloc;  // memsets cover every allocated plane
   dim3 grid;
   const int chunks = obs_grid(c, a, nv, grid);
-  if (!c->dense) {
-    for (int s = 0; s < S; s++)
-      CUDA_TRY(cudaMemsetAsync(Gq + (size_t)s * plane_stride, 0, (size_t)rows_padded * c->ldg, c->stream));
-  } else if (rows_padded > 3 * nv) {  // zero the K-padding rows of every plane
-    for (int s = 0; s < S; s++)
-      CUDA_TRY(cudaMemsetAsync(Gq + (size_t)s * plane_stride + (size_t)3 * nv * c->ldg, 0,
-                               (size_t)(rows_padded - 3 * nv) * c->ldg, c->stream));
+  if (!(skip && !fused)) {  // the re-armed sweep 2 finds the padding already zeroed by the fused sweep
+    if (!c->dense) {
+      for (int s = 0; s < S; s++)
+        CUDA_TRY(cudaMemsetAsync(Gq + (size_t)s * plane_stride, 0, (size_t)rows_padded * c->ldg, c->stream));
+    } else if (rows_padded > 3 * nv) {  // zero the K-padding rows of every plane
+      for (int s = 0; s < S; s++)
+        CUDA_TRY(cudaMemsetAsync(Gq + (size_t)s * plane_stride + (size_t)3 * nv * c->ldg, 0,
+                                 (size_t)(rows_padded - 3 * nv) * c->ldg, c->stream));
+    }
   }
-  (void)chunks; (void)first_batch;
-  if (c->dense) obs_pass_kernel<true, OBS_INT8><<<grid, 128, 0, c->stream>>>(a);
-  else obs_pass_kernel<false, OBS_INT8><<<grid, 128, 0, c->stream>>>(a);
-  c->launches += 1;
+  if (fused) {
+    if (c->dense) obs_pass_kernel<true, OBS_FUSED><<<grid, 128, 0, c->stream>>>(a);
+    else obs_pass_kernel<false, OBS_FUSED><<<grid, 128, 0, c->stream>>>(a);
+    const int total = BALM_ACC * c->Np;
+    obs_reduce_kernel<<<(total + 255) / 256, 256, 0, c->stream>>>(c->obs_part, chunks, total, c->accum,
+                                                                  c->accum_batch, first_batch ? 0 : 1);
+    c->launches += 2;
+  } else {
+    if (c->dense) obs_pass_kernel<true, OBS_INT8><<<grid, 128, 0, c->stream>>>(a);
+    else obs_pass_kernel<false, OBS_INT8><<<grid, 128, 0, c->stream>>>(a);
+    c->launches += 1;
+  }
   CUDA_TRY(cudaGetLastError());
   return BALM_OK;
 }

@@ -64,6 +64,8 @@ struct balm_ctx {
   // ---- evaluation workspaces ----
   int64_t VB = 0;                 // voxels per batch
   double *stats = nullptr;        // [VB][20]
+  double *stats_trial = nullptr;  // [M][20] stats of the LM trial poses (single-batch problems): an accepted step
+                                  // hands them to the next evaluation instead of recomputing them
   double *G = nullptr;            // [3*VB][ldg] fp64 scaled factor matrix G' (MN-major: pose index contiguous)
   int obs_chunks = 0;
   double *obs_part = nullptr;     // [obs_chunks][27][Np]
@@ -236,12 +238,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 #endif  // __CUDACC__
 
 // ---------------- kernel launchers (defined in the .cu files) ----------------
-int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool store_stats, bool use_fix,
+int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, double *stats_out, bool use_fix,
                        double *residual_out_dev);
 int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch, const double *sc,
-                    int8_t *Gq, int64_t plane_stride, const int *S_dev, int S_alloc, int64_t rows_padded);
+                    int8_t *Gq, int64_t plane_stride, const int *S_dev, int S_alloc, int64_t rows_padded, bool fused,
+                    const int *skip);
 int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch);
 int launch_assemble(balm_ctx *c);

@@ -683,16 +683,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   syrk_tc_body<true>(tmap, tmap_half, a);
 }
 
-// Column scales and the digit-plane count, decided ON THE DEVICE from the current data (one block):
+// Column scales and digit-plane count of one batch, decided ON THE DEVICE from the column maxima and sums of squares
+// of G' (one block):
 //   e_j = max|G'_j| / sqrt(sum G'_j^2)  is the concentration of column j (1 = a single dominant entry, ~1/sqrt(rows)
 //   for evenly spread columns); rounding G' to 2^-(8S-2) of the column maximum perturbs H_ij by about
 //   2^-(8S-2) * e * sqrt(H_ii H_jj).  S = 3 is used when that stays below 5e-9 for every column, else S = 4
 //   (forced_S > 0 overrides).  Then sc_j = 2^p with colmax_j * sc_j in [2^(8S-3), 2^(8S-2)), isc_j = 256^(S-1)/sc_j.
+//   fresh values (scale 2^p with |G'_j| 2^p in [2^(8S-3), 2^(8S-2)), S by the concentration rule) always go to
+//   sc_next/isc_next/S_next (when given): they are what the NEXT evaluation of the same voxels speculates with.
+//   spec = 0: they are also the scales of this batch (sc/isc/S_dev), *spec_ok = 0 -> the OBS_INT8 sweep runs.
+//   spec = 1: the digit planes were ALREADY written by the fused sweep with sc/S_dev. They stand (*spec_ok = 1)
+//             iff S is still what the rule asks for and every column (a) stayed inside the balanced-digit range,
+//             |G'_j| sc_j < 0.99 * 2^(8S-1), and (b) kept a rounding unit 1/sc_j <= 1e-8 sqrt(sum G'_j^2) -- the bound
+//             the S rule itself guarantees. Otherwise the fresh values are adopted and sweep 2 is re-armed.
 __global__ void __launch_bounds__(1024) tc_scale_kernel(const unsigned long long *colmax_bits, const double *accum_batch,
                                                         int Np, int n, double *sc, double *isc, int ldq, int forced_S,
-                                                        int *S_dev) {
+                                                        int *S_dev, int spec, double *sc_next, double *isc_next,
+                                                        int *S_next, int *spec_ok) {
   __shared__ double red[32];
-  __shared__ int S_sh;
+  __shared__ int S_sh, bad_sh;
+  if (threadIdx.x == 0) bad_sh = 0;
   double emax = 0.0;
   for (int j = threadIdx.x; j < n; j += 1024) {
     const double m = __longlong_as_double((long long)colmax_bits[j]);
@@ -709,23 +719,56 @@ __global__ void __launch_bounds__(1024) tc_scale_kernel(const unsigned long long
     int S = (e * (1.0 / 4194304.0) <= 5e-9) ? 3 : 4;  // 2^-22 * e
     if (forced_S > 0) S = forced_S;
     S_sh = S;
-    *S_dev = S;
+    if (spec && *S_dev != S) bad_sh = 1;
   }
   __syncthreads();
   const int S = S_sh;
+  double *fsc = sc_next ? sc_next : sc, *fisc = sc_next ? isc_next : isc;  // where the fresh values go first
+  int bad = 0;
   for (int j = threadIdx.x; j < ldq; j += 1024) {
     const double m = __longlong_as_double((long long)colmax_bits[j]);
-    if (!(m > 0.0) || !(m < 1e300)) {
-      sc[j] = 0.0;
-      isc[j] = 0.0;
+    const bool live = (m > 0.0) && (m < 1e300);
+    if (spec && live && j < n) {
+      const double used = sc[j];
+      const double h = accum_batch[(size_t)(27 + j % 6) * Np + j / 6];
+      if (!(used > 0.0) || !(m * used < 0.99 * ldexp(1.0, 8 * S - 1)) || !(1.0 <= 1e-8 * sqrt(h) * used)) bad = 1;
+    }
+    if (!live) {
+      fsc[j] = 0.0;
+      fisc[j] = 0.0;
       continue;
     }
     int e;
     frexp(m, &e);  // m = f * 2^e, f in [0.5, 1)  ->  m < 2^e
     const int p = 8 * S - 2 - e;
-    sc[j] = ldexp(1.0, p);
-    isc[j] = ldexp(1.0, 8 * (S - 1) - p);
+    fsc[j] = ldexp(1.0, p);
+    fisc[j] = ldexp(1.0, 8 * (S - 1) - p);
   }
+  if (bad) atomicOr(&bad_sh, 1);
+  __syncthreads();
+  const bool keep = spec && !bad_sh;
+  if (sc_next && !keep) {
+    for (int j = threadIdx.x; j < ldq; j += 1024) {
+      sc[j] = sc_next[j];
+      isc[j] = isc_next[j];
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (!keep) *S_dev = S;
+    if (S_next) *S_next = S;
+    *spec_ok = keep ? 1 : 0;
+  }
+}
+
+// start of a speculative evaluation: the scales found by the previous one become the ones in use
+__global__ void tc_adopt_kernel(double *sc, double *isc, int *S_dev, const double *sc_next, const double *isc_next,
+                                const int *S_next, int ldq) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < ldq) {
+    sc[j] = sc_next[j];
+    isc[j] = isc_next[j];
+  }
+  if (j == 0) *S_dev = *S_next;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -743,6 +786,11 @@ struct TcState {
   int n_pairs2 = 0;
   bool use_2sm = false;
   double *sc = nullptr, *isc = nullptr;
+  double *sc_next = nullptr, *isc_next = nullptr;  // fresh scales of the last full-range evaluation (speculation)
+  int *S_next = nullptr, *spec_ok = nullptr;
+  bool spec_ready = false;                         // sc_next/S_next describe the currently registered voxels
+  bool spec_enabled = true;                        // BALM_NO_SPEC=1 keeps the two-sweep path
+  bool last_spec = false;                          // the batch in flight used the fused sweep
   unsigned long long *colmax = nullptr;
   int *err = nullptr;
   int64_t rows_alloc = 0;
@@ -769,6 +817,12 @@ int tensor_syrk_init(balm_ctx *c) {
   CUDA_TRY(cudaMalloc((void **)&st->S_dev, sizeof(int)));
   CUDA_TRY(cudaMalloc((void **)&st->sc, sizeof(double) * ldq));
   CUDA_TRY(cudaMalloc((void **)&st->isc, sizeof(double) * ldq));
+  CUDA_TRY(cudaMalloc((void **)&st->sc_next, sizeof(double) * ldq));
+  CUDA_TRY(cudaMalloc((void **)&st->isc_next, sizeof(double) * ldq));
+  CUDA_TRY(cudaMalloc((void **)&st->S_next, sizeof(int)));
+  CUDA_TRY(cudaMalloc((void **)&st->spec_ok, sizeof(int)));
+  CUDA_TRY(cudaMemset(st->spec_ok, 0, sizeof(int)));
+  st->spec_enabled = getenv("BALM_NO_SPEC") == nullptr;
   CUDA_TRY(cudaMalloc((void **)&st->colmax, sizeof(unsigned long long) * ldq));
   CUDA_TRY(cudaMalloc((void **)&st->err, sizeof(int)));
   CUDA_TRY(cudaMemset(st->err, 0, sizeof(int)));
@@ -859,6 +913,7 @@ int tensor_syrk_init(balm_ctx *c) {
 void tensor_syrk_free(balm_ctx *c) {
   if (c->tmap) {
     TcState *st = static_cast<TcState *>(c->tmap);
+    cudaFree(st->sc_next); cudaFree(st->isc_next); cudaFree(st->S_next); cudaFree(st->spec_ok);
     cudaFree(st->sc); cudaFree(st->isc); cudaFree(st->colmax); cudaFree(st->err); cudaFree(st->S_dev); cudaFree(st->pairs); cudaFree(st->pairs2);
     delete st;
     c->tmap = nullptr;
@@ -877,13 +932,28 @@ int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1
   const int64_t rows = 3 * (v1 - v0);
   const int64_t rows_padded = (rows + KS - 1) / KS * KS;
   CUDA_TRY(cudaMemsetAsync(st->colmax, 0, sizeof(unsigned long long) * ldq, c->stream));
-  int rc = launch_obs_colmax(c, poses, v0, v1, first_batch);
+  const bool full = (v0 == 0 && v1 == c->M);  // only full-range evaluations feed / use the speculation
+  const bool spec = full && st->spec_ready && st->spec_enabled;
+  const int64_t plane_stride = (int64_t)st->rows_alloc * ldq;
+  int rc;
+  if (spec) {  // one sweep with the previous evaluation's scales; sweep 2 below only runs if tc_scale_kernel re-arms it
+    tc_adopt_kernel<<<(ldq + 255) / 256, 256, 0, c->stream>>>(st->sc, st->isc, st->S_dev, st->sc_next, st->isc_next,
+                                                              st->S_next, ldq);
+    c->launches += 1;
+    rc = launch_obs_int8(c, poses, v0, v1, first_batch, st->sc, c->Gq, plane_stride, st->S_dev, SMAX, rows_padded, true,
+                         nullptr);
+  } else {
+    rc = launch_obs_colmax(c, poses, v0, v1, first_batch);
+  }
   if (rc != BALM_OK) return rc;
   tc_scale_kernel<<<1, 1024, 0, c->stream>>>(st->colmax, c->accum_batch, c->Np, c->n, st->sc, st->isc, ldq,
-                                             st->forced_S, st->S_dev);
-  rc = launch_obs_int8(c, poses, v0, v1, first_batch, st->sc, c->Gq, (int64_t)st->rows_alloc * ldq, st->S_dev, SMAX,
-                       rows_padded);
+                                             st->forced_S, st->S_dev, spec ? 1 : 0, full ? st->sc_next : nullptr,
+                                             full ? st->isc_next : nullptr, full ? st->S_next : nullptr, st->spec_ok);
+  rc = launch_obs_int8(c, poses, v0, v1, first_batch, st->sc, c->Gq, plane_stride, st->S_dev, SMAX, rows_padded, false,
+                       spec ? st->spec_ok : nullptr);
   if (rc != BALM_OK) return rc;
+  if (full) st->spec_ready = true;
+  st->last_spec = spec;
   CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
   TcArgs a{rows_padded, c->syrk_nb, c->syrk_tiles, c->syrk_splits, st->S_dev, st->isc, c->syrk_part,
            first_batch ? 0 : 1, st->err, getenv("BALM_TC_NO_COLLECTOR") ? 0 : 1, st->pairs, st->n_pairs};
@@ -922,9 +992,12 @@ int tensor_syrk_check(balm_ctx *c) {
   if (!st) return BALM_OK;
   int e = 0;
   CUDA_TRY(cudaMemcpyAsync(&e, st->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int ok = 0;
   CUDA_TRY(cudaMemcpyAsync(&st->last_S, st->S_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(&ok, st->spec_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->tm.digit_planes = st->last_S;
+  if (st->last_spec) (ok ? c->tm.single_sweeps : c->tm.redone_sweeps) += 1;
   if (e != 0) {
     balm_set_error("tcgen05 SYRK pipeline timed out (mbarrier wait bound exceeded)");
     return BALM_ERR_CUDA;

@@ -318,18 +318,22 @@ def main():
     if args.precision == "fp64":
         roof["frac_of_fp64_nominal_40tf"] = ach_tf / 40.0
     res_ms = tm["ms_residual"] / max(tm["n_residual"], 1)
-    stats_ms = tm["ms_stats"] / n_eval
+    stats_ms = tm["ms_stats"] / max(tm["n_stats"], 1) if tm["n_stats"] else res_ms
     obs_ms = tm["ms_obs"] / n_eval
     if args.precision == "tensor":
-        gout, gnote = 72.0, ("80 B/obs read (counted once; the column-max sweep re-reads it) + 72 B/obs written "
-                             "(18 values x 4 int8 digit planes)")
+        gout = 18.0 * tm["digit_planes"]
+        gnote = (f"80 B/obs read (counted once) + {gout:.0f} B/obs written (18 values x {tm['digit_planes']} int8 digit "
+                 f"planes); {tm['single_sweeps']} of {n_eval} evaluations needed one sweep (scales speculated from the "
+                 f"previous evaluation and accepted), {tm['redone_sweeps']} re-ran the digit sweep, the rest swept twice")
     else:
         gout, gnote = 144.0, "80 B/obs read + 144 B/obs fp64 G' written"
     hbm = {
         "residual_pass": {"bound": "hbm", "achieved": obs_bytes / (res_ms * 1e-3) / 1e9, "peak": pk["hbm"],
                           "unit": "GB/s", "frac": obs_bytes / (res_ms * 1e-3) / 1e9 / pk["hbm"], "ms": res_ms},
         "voxel_stats": {"bound": "hbm", "achieved": obs_bytes / (stats_ms * 1e-3) / 1e9, "peak": pk["hbm"],
-                        "unit": "GB/s", "frac": obs_bytes / (stats_ms * 1e-3) / 1e9 / pk["hbm"], "ms": stats_ms},
+                        "unit": "GB/s", "frac": obs_bytes / (stats_ms * 1e-3) / 1e9 / pk["hbm"], "ms": stats_ms,
+                        "note": f"ran in {tm['n_stats']} of {n_eval} evaluations; the others took the eigen data "
+                                f"from the residual pass of the accepted step (same kernel, same poses)"},
         "obs_pass": {"bound": "hbm", "achieved": (obs_bytes + gout * M * N) / (obs_ms * 1e-3) / 1e9,
                      "peak": pk["hbm"], "unit": "GB/s",
                      "frac": (obs_bytes + gout * M * N) / (obs_ms * 1e-3) / 1e9 / pk["hbm"], "ms": obs_ms,
@@ -364,6 +368,8 @@ def main():
         "job_iter_per_s": K / (ms_max * 1e-3),
         "phases_ms": phases, "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": tm["launches"], "clocks": clocks,
+        "sweeps": {"evaluations": tm["n_eval"], "stats_passes": tm["n_stats"], "single_sweeps": tm["single_sweeps"],
+                   "redone_sweeps": tm["redone_sweeps"]},
         "lm_trace": [{"r1": t_["r1"], "r2": t_["r2"], "acc": t_["accepted"]} for t_ in trace[:4]],
     }
     print(json.dumps(line), flush=True)

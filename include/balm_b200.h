@@ -75,6 +75,11 @@ typedef struct {
   int launches;   /* kernels launched by the library since balm_reset_counters() */
   int n_eval, n_solve, n_residual;
   int digit_planes; /* tensor path: int8 digit planes used by the last evaluation (3 or 4, chosen on the device) */
+  int single_sweeps; /* tensor path: evaluations whose one fused observation sweep (column scales speculated from the
+                        previous evaluation) was accepted ... */
+  int redone_sweeps; /* ... and those whose scales failed the check, so the digit-plane sweep ran again */
+  int n_stats;       /* evaluations that ran the per-voxel eigen pass themselves (ms_stats sums only these): inside
+                        balm_damping_iter the residual pass of the previous step usually hands its results over */
 } balm_timings;
 
 const char *balm_last_error(void);

@@ -68,6 +68,36 @@ def test_evaluate_matches_oracle(n_poses, n_planes, drop, with_fix, prec):
     _check_eval(c, o, sc["poses_gt"], tolr=1e-10, tolH=TOLH[prec])
 
 
+@pytest.mark.parametrize("drop", [0.0, 0.4])
+def test_tensor_single_sweep_speculation(drop):
+    """Tensor path: from the second full evaluation on, the column scales come from the previous evaluation and ONE
+    observation sweep writes the digit planes; the device-side check either accepts it or re-runs the digit sweep."""
+    sc = scenes.make_scene(n_poses=24, n_planes=150, seed=33, drop=drop)
+    c, o = _ctx(sc, 1), _oracle(sc)
+    c.reset_counters()
+    H0, g0, r0 = _check_eval(c, o, sc["poses_init"], tolH=TOLH[1])            # two sweeps (nothing to speculate from)
+    tm = c.timings()
+    assert tm["single_sweeps"] == 0 and tm["redone_sweeps"] == 0
+    H1, g1, r1 = _check_eval(c, o, sc["poses_init"], tolH=TOLH[1])            # same poses -> same scales, accepted
+    tm = c.timings()
+    assert tm["single_sweeps"] == 1 and tm["redone_sweeps"] == 0
+    assert np.array_equal(H0, H1) and np.array_equal(g0, g1) and r0 == r1
+    rng = np.random.default_rng(3)
+    near = sc["poses_init"].copy()
+    near[:, 9:] += rng.normal(0, 1e-3, (len(near), 3))                        # an LM-step-sized move
+    _check_eval(c, o, near, tolH=TOLH[1])
+    tm = c.timings()
+    assert tm["single_sweeps"] + tm["redone_sweeps"] == 2
+    far = sc["poses_init"].copy()
+    far[:, 9:] *= 40.0                                                         # column maxima grow far beyond the 2x headroom
+    far[:, 9:] += 25.0
+    _check_eval(c, o, far, tolH=TOLH[1], tolr=1e-10)
+    tm = c.timings()
+    assert tm["redone_sweeps"] >= 1 and tm["single_sweeps"] + tm["redone_sweeps"] == 3
+    _check_eval(c, o, sc["poses_init"], tolH=TOLH[1])                          # and back: scales shrink by the same factor
+    assert c.timings()["redone_sweeps"] >= 2
+
+
 def test_voxel_range_semantics():
     sc = scenes.make_scene(n_poses=10, n_planes=60, seed=22)
     c, o = _ctx(sc), _oracle(sc)
