@@ -154,7 +154,11 @@ extern "C" int balm_create(balm_ctx **out, int n_poses, int device, int precisio
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
-  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  int prio_least = 0, prio_greatest = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
+  CUDA_TRY(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_least));
+  for (auto &e : c->sev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   TRY(factor_kernels_setup());
   TRY(syrk_f64_setup());
   TRY(ldlt_setup());
@@ -164,10 +168,10 @@ extern "C" int balm_create(balm_ctx **out, int n_poses, int device, int precisio
   TRY(dev_alloc(&c->H, n * n + n + 8));
   c->g = c->H + n * n;
   TRY(dev_alloc(&c->A, n * n));
-  TRY(dev_alloc(&c->W, n * BALM_NB));
+  TRY(dev_alloc(&c->W, 2 * n * BALM_NB));
   TRY(dev_alloc(&c->dx, n));
   TRY(dev_alloc(&c->dvec, n));
-  TRY(dev_alloc(&c->scal, 16));
+  TRY(dev_alloc(&c->scal, 32));
   TRY(dev_alloc(&c->flags, 4));
   TRY(dev_alloc(&c->accum, (size_t)BALM_ACC * c->Np));
   TRY(dev_alloc(&c->accum_batch, (size_t)BALM_ACC * c->Np));
@@ -192,6 +196,8 @@ extern "C" int balm_destroy(balm_ctx *c) {
   if (c->solve_graph) cudaGraphExecDestroy((cudaGraphExec_t)c->solve_graph);
   cudaFreeHost(c->h_scal); cudaFreeHost(c->h_flags);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto &e : c->sev) if (e) cudaEventDestroy(e);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
   return BALM_OK;
@@ -433,7 +439,7 @@ static int allreduce_sum(balm_ctx *c, double *buf, size_t count) {
 
 // H, g, r of voxels [head,end) at device poses `poses`; result in c->H | c->g | c->scal[0] (all-reduced).
 // stats_cached: c->stats already holds the per-voxel eigen data of exactly these poses (left there by the residual
-// pass of an accepted LM step, or by the evaluation before a rejected one) and c->scal[4] this rank's residual.
+// pass of an accepted LM step, or by the evaluation before a rejected one) and c->scal[BALM_SCAL_RCUR] this rank's residual.
 static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t end, bool include_fix,
                         bool stats_cached = false) {
   if (!c->obs) { balm_set_error("no voxels registered"); return BALM_ERR_INVALID; }
@@ -450,7 +456,7 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
   for (int64_t v0 = head; v0 < end; v0 += c->VB) {
     const int64_t v1 = std::min(end, v0 + c->VB);
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    if (stats_cached) CUDA_TRY(cudaMemcpyAsync(r_dev, c->scal + 4, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (stats_cached) CUDA_TRY(cudaMemcpyAsync(r_dev, c->scal + BALM_SCAL_RCUR, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     else TRY(launch_voxel_stats(c, poses, v0, v1, c->stats, include_fix, r_dev));
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     if (c->prec == BALM_PREC_TENSOR) {
@@ -469,7 +475,7 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
     if (c->prec == BALM_PREC_TENSOR) TRY(tensor_syrk_check(c));
     first = false;
   }
-  CUDA_TRY(cudaMemcpyAsync(c->scal + 4, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // local, pre all-reduce
+  CUDA_TRY(cudaMemcpyAsync(c->scal + BALM_SCAL_RCUR, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // local, pre all-reduce
   CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
   TRY(launch_assemble(c));
   CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
@@ -489,7 +495,7 @@ static int residual_dev(balm_ctx *c, const double *poses, double *host_out, bool
   CUDA_TRY(cudaEventRecord(c->ev[7], c->stream));
   CUDA_TRY(cudaMemsetAsync(r_dev, 0, sizeof(double), c->stream));
   TRY(launch_voxel_stats(c, poses, 0, c->M, keep_stats ? c->stats_trial : nullptr, true, r_dev));
-  CUDA_TRY(cudaMemcpyAsync(c->scal + 3, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // local, pre all-reduce
+  CUDA_TRY(cudaMemcpyAsync(c->scal + BALM_SCAL_RTRIAL, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // local, pre all-reduce
   TRY(allreduce_sum(c, r_dev, 1));
   CUDA_TRY(cudaEventRecord(c->ev[8], c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->h_scal + 2, r_dev, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -603,7 +609,7 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
       std::swap(c->poses, c->poses_trial);
       if (hand_over) {
         std::swap(c->stats, c->stats_trial);
-        CUDA_TRY(cudaMemcpyAsync(c->scal + 4, c->scal + 3, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->scal + BALM_SCAL_RCUR, c->scal + BALM_SCAL_RTRIAL, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
       }
       stats_cached = hand_over;
       const double rho = q / q1;

@@ -6,6 +6,8 @@
 #include <string>
 #include "../../include/balm_b200.h"
 
+#define BALM_SCAL_RCUR 16
+#define BALM_SCAL_RTRIAL 17
 #define BALM_STATS_STRIDE 20  // doubles per voxel in the stats table
 #define BALM_ACC 33           // per-pose accumulators of the observation pass: g(6) + sym 6x6 diag block (21)
                               // + exact fp64 sums of squares of the 6 G' columns (diagonal of G'^T G')
@@ -29,6 +31,9 @@ void balm_set_error(const std::string &s);
 struct balm_ctx {
   int N = 0, n = 0, ldg = 0, Np = 0, device = 0, prec = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream of the solve's look-ahead (lower priority)
+  cudaEvent_t sev[3] = {nullptr, nullptr, nullptr};  // panel done / rest done (two parities)
+  bool solve_lookahead = true;
   int sm_count = 148;
 
   // ---- registered problem (device) ----
@@ -48,7 +53,7 @@ struct balm_ctx {
   double *poses = nullptr, *poses_trial = nullptr;  // [12N]
   double *H = nullptr, *g = nullptr;                // [n*n + n + 8] contiguous: H | g | r  (one all-reduce)
   double *A = nullptr;                              // [n*n] factor workspace
-  double *W = nullptr;                              // [n*NB] panel * D
+  double *W = nullptr;                              // [2][n*NB] panel * D (double-buffered by step parity)
   double *dx = nullptr;                             // [n]
   double *dvec = nullptr;                           // [n] diag(H)
   double *Xinv = nullptr;                           // [panels][64*64] inverses of the unit-lower diagonal blocks
@@ -56,7 +61,8 @@ struct balm_ctx {
   double *sol = nullptr;                            // [n] right-hand side / forward-substitution vector
   void *solve_graph = nullptr;                      // cudaGraphExec_t of the solve sequence
   int solve_launches = 0;
-  double *scal = nullptr;                           // device scalars [16]
+  double *scal = nullptr;                           // device scalars [32]: 0 r(eval) 1 q1 2 r(residual) 3 u 4..15 gauge
+                                                    // snapshot, 16/17 this rank's residual at the current / trial poses
   double *h_scal = nullptr;                         // pinned host mirror [16]
   int *flags = nullptr;                             // device flags [4] (0: ldlt bad pivot)
   int *h_flags = nullptr;

@@ -275,14 +275,19 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 }
 
 // Trailing update A22 -= L21 * W^T on 128x128 tiles of the lower triangle with fp64 tensor-core MMAs
-// (mma.sync.m8n8k4.f64, 8 warps x (64x32) warp tiles, cp.async double-buffered k slabs of 16).
-__global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double *W, int n, int j0, int nbw) {
+// (mma.sync.m8n8k4.f64, 8 warps x (64x32) warp tiles, the whole 64-wide k slab staged by one cp.async round).
+// The update of a panel step is issued in two parts (look-ahead): the STRIP (strip = 1: the NB columns of the next
+// panel, one tile per 128 rows, stores masked to col < base + NB) stays on the critical path; the REST (strip = 0,
+// base moved past the strip) runs on the side stream while the next diagonal block and panel are factored.
+__global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double *W, int n, int j0, int nbw, int base,
+                                                         int strip) {
   extern __shared__ __align__(16) double dyn_smem[];
-  const int base = j0 + nbw;
   int t = blockIdx.x, tr = 0;
-  while (t >= tr + 1) { t -= tr + 1; tr++; }
+  if (strip) { tr = t; t = 0; }
+  else while (t >= tr + 1) { t -= tr + 1; tr++; }
   const int tc = t;  // tc <= tr
   const int r0 = base + tr * UT, c0 = base + tc * UT;
+  const int climit = strip ? base + NB : n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3, fr = lane >> 2, fk = lane & 3;
   double acc[8][4][2];
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double
       const bool kv = k0 + k < nbw;
       if (kv && r0 + rr < n) cp_async16(sL + k * ULDS + rr, A + (size_t)(j0 + k0 + k) * n + r0 + rr);
       else *reinterpret_cast<double2 *>(sL + k * ULDS + rr) = make_double2(0.0, 0.0);
-      if (kv && c0 + rr < n) cp_async16(sW + k * ULDS + rr, W + (size_t)(k0 + k) * n + c0 + rr);
+      if (kv && c0 + rr < climit) cp_async16(sW + k * ULDS + rr, W + (size_t)(k0 + k) * n + c0 + rr);
       else *reinterpret_cast<double2 *>(sW + k * ULDS + rr) = make_double2(0.0, 0.0);
     }
   };
@@ -342,14 +347,14 @@ __global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int col = c0 + wn * 32 + j * 8 + 2 * fk;
-      cv[j][0] = (row < n && col < n && row >= col) ? A[(size_t)col * n + row] : 0.0;
-      cv[j][1] = (row < n && col + 1 < n && row >= col + 1) ? A[(size_t)(col + 1) * n + row] : 0.0;
+      cv[j][0] = (row < n && col < climit && row >= col) ? A[(size_t)col * n + row] : 0.0;
+      cv[j][1] = (row < n && col + 1 < climit && row >= col + 1) ? A[(size_t)(col + 1) * n + row] : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int col = c0 + wn * 32 + j * 8 + 2 * fk;
-      if (row < n && col < n && row >= col) A[(size_t)col * n + row] = cv[j][0] - acc[i][j][0];
-      if (row < n && col + 1 < n && row >= col + 1) A[(size_t)(col + 1) * n + row] = cv[j][1] - acc[i][j][1];
+      if (row < n && col < climit && row >= col) A[(size_t)col * n + row] = cv[j][0] - acc[i][j][0];
+      if (row < n && col + 1 < climit && row >= col + 1) A[(size_t)(col + 1) * n + row] = cv[j][1] - acc[i][j][1];
     }
   }
 }
@@ -360,33 +365,55 @@ __global__ void rhs_init_kernel(const double *g, double *sol, int n) {
   if (i < n) sol[i] = -g[i];
 }
 
-// Backward substitution L^T x = w (w = d^-1 y, scaled beforehand), block j descending: x_j = X_j^T w_j, then
-// w_c -= sum_r L[j0+r][c] x_j[r] for every column c left of the block. One small grid per block; every CTA
-// recomputes the 64x64 mat-vec x_j (4096 FMAs) instead of synchronising on it.
-__global__ void __launch_bounds__(256) ldl_back_kernel(const double *A, int n, int j0, int nbw, const double *Xcm,
+// Backward substitution L^T x = w (w = d^-1 y, scaled beforehand), block groups descending. One launch handles up to
+// four 64-row blocks [g_lo, g_lo+G): every CTA first solves the group's own triangle redundantly (x_b = X_b^T w_b,
+// then w_c -= L[b rows][c] x_b for the group's lower columns; a warp per column, rows contiguous -> coalesced), which
+// replaces three kernel boundaries of the serial chain by block barriers, and then applies the group's G rows to its
+// share of the columns left of the group (w_c -= sum_r L[g_lo+r][c] x[r], up to 2 KB contiguous per column).
+constexpr int BACK_GROUP = 4;
+__global__ void __launch_bounds__(256) ldl_back_kernel(const double *A, int n, int g_lo, int G, const double *Xcm,
                                                        double *sol, double *x) {
-  __shared__ double wj[NB], xj[NB];
-  const int tid = threadIdx.x;
-  if (tid < NB) wj[tid] = tid < nbw ? sol[j0 + tid] : 0.0;
+  __shared__ double w[BACK_GROUP * NB], xs[BACK_GROUP * NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  w[tid] = tid < G ? sol[g_lo + tid] : 0.0;
+  xs[tid] = 0.0;
   __syncthreads();
-  if (tid < NB) {  // x_j[c] = sum_r X[r][c] w[r], X column-major: contiguous in r
-    double s = 0.0;
-    const double *xc = Xcm + tid * NB;
-#pragma unroll 8
-    for (int r = 0; r < NB; r++) s += xc[r] * wj[r];
-    xj[tid] = s;
-    if (blockIdx.x == 0 && tid < nbw) x[j0 + tid] = s;
+  const int nblk = (G + NB - 1) / NB;
+  for (int b = nblk - 1; b >= 0; b--) {
+    const int j = NB * b;
+    const int bw = G - j < NB ? G - j : NB;
+    const double *Xb = Xcm + (size_t)b * NB * NB;  // column-major X = L_bb^-1 (identity-padded when bw < NB)
+#pragma unroll
+    for (int q = 0; q < 8; q++) {  // x_b[c] = sum_r X[r][c] w_b[r]
+      const int c = warp * 8 + q;
+      double sacc = Xb[c * NB + lane] * w[j + lane] + Xb[c * NB + lane + 32] * w[j + lane + 32];
+      sacc = warp_sum(sacc);
+      if (lane == 0) xs[j + c] = c < bw ? sacc : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int cl = warp; cl < j; cl += 8) {  // the group's columns below block b
+      const double *col = A + (size_t)(g_lo + cl) * n + g_lo + j;
+      double sacc = 0.0;
+      if (lane < bw) sacc = col[lane] * xs[j + lane];
+      if (lane + 32 < bw) sacc += col[lane + 32] * xs[j + lane + 32];
+      sacc = warp_sum(sacc);
+      if (lane == 0) w[cl] -= sacc;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // one warp per column: the 64 contiguous doubles L[j0..j0+63][c] are one coalesced 512-byte request
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int c = (blockIdx.x * 8 + warp) * 4; c < j0 && c < (blockIdx.x * 8 + warp) * 4 + 4; c++) {
-    const double *col = A + (size_t)c * n + j0;
-    double s = 0.0;
-    if (lane < nbw) s = col[lane] * xj[lane];
-    if (lane + 32 < nbw) s += col[lane + 32] * xj[lane + 32];
-    s = warp_sum(s);
-    if (lane == 0) sol[c] -= s;
+  if (blockIdx.x == 0 && tid < G) x[g_lo + tid] = xs[tid];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {  // columns left of the group: 8 warps x 4 columns per CTA
+    const int c = (blockIdx.x * 8 + warp) * 4 + q;
+    if (c >= g_lo) break;
+    const double *col = A + (size_t)c * n + g_lo;
+    double sacc = 0.0;
+#pragma unroll
+    for (int r = lane; r < BACK_GROUP * NB; r += 32)
+      if (r < G) sacc += col[r] * xs[r];
+    sacc = warp_sum(sacc);
+    if (lane == 0) sol[c] -= sacc;
   }
 }
 
@@ -467,36 +494,63 @@ __global__ void gauge_kernel(double *poses, const double *pose0_snapshot, int N,
 
 constexpr int DIAG_SMEM = (2 * NB * (NB + 1) + NB * 17 + 32 + NB) * (int)sizeof(double);
 
+// The factorisation loop with look-ahead. Main stream (high priority): diag(k) -> panel(k) -> strip(k) -> diag(k+1);
+// side stream: rest(k) after panel(k). Hazards: strip(k) and rest(k-1) both update the columns of panel k+1, and
+// panel(k+1) overwrites the W buffer rest(k-1) reads (W is double-buffered by step parity) -> strip(k) waits for
+// rest(k-1). rest(k) touches only columns right of panel k+1, which diag/panel(k+1) never access.
 static int enqueue_solve(balm_ctx *c) {
   const int n = c->n;
-  cudaStream_t st = c->stream;
+  cudaStream_t st = c->stream, side = c->stream2;
   dim3 g1((n + 255) / 256, n);
   damp_copy_kernel<<<g1, 256, 0, st>>>(c->H, c->A, c->dvec, n, c->scal + 3);
   rhs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->g, c->sol, n);
   const int panel_smem = 2 * NB * (NB + 4) * (int)sizeof(double);
   const int update_smem = USTAGE * (int)sizeof(double);
   int launches = 2;
+  int pending_rest = -1;  // parity of the side-stream event still to be waited for
   for (int j0 = 0, pi = 0; j0 < n; j0 += NB, pi++) {
     const int nbw = (n - j0 < NB) ? n - j0 : NB;
     double *X = c->Xinv + (size_t)pi * NB * NB;
+    double *W = c->W + (size_t)(pi & 1) * n * NB;
     ldl_diag_kernel<<<1, 256, DIAG_SMEM, st>>>(c->A, n, j0, nbw, X, c->dinv, c->sol, c->flags);
     launches++;
     const int m = n - j0 - nbw;
     if (m > 0) {
       const int mt = (m + NB - 1) / NB, mu = (m + UT - 1) / UT;
-      ldl_panel_kernel<<<mt, 256, panel_smem, st>>>(c->A, c->W, n, j0, nbw, X, c->dinv, c->sol);
-      ldl_update_kernel<<<mu * (mu + 1) / 2, 256, update_smem, st>>>(c->A, c->W, n, j0, nbw);
-      launches += 2;
+      ldl_panel_kernel<<<mt, 256, panel_smem, st>>>(c->A, W, n, j0, nbw, X, c->dinv, c->sol);
+      launches++;
+      const int base = j0 + nbw;
+      if (!c->solve_lookahead) {
+        ldl_update_kernel<<<mu * (mu + 1) / 2, 256, update_smem, st>>>(c->A, W, n, j0, nbw, base, 0);
+        launches++;
+        continue;
+      }
+      CUDA_TRY(cudaEventRecord(c->sev[0], st));
+      if (pending_rest >= 0) CUDA_TRY(cudaStreamWaitEvent(st, c->sev[1 + pending_rest], 0));
+      pending_rest = -1;
+      ldl_update_kernel<<<mu, 256, update_smem, st>>>(c->A, W, n, j0, nbw, base, 1);
+      launches++;
+      const int m2 = m - NB;
+      if (m2 > 0) {
+        const int mu2 = (m2 + UT - 1) / UT;
+        CUDA_TRY(cudaStreamWaitEvent(side, c->sev[0], 0));
+        ldl_update_kernel<<<mu2 * (mu2 + 1) / 2, 256, update_smem, side>>>(c->A, W, n, j0, nbw, base + NB, 0);
+        launches++;
+        CUDA_TRY(cudaEventRecord(c->sev[1 + (pi & 1)], side));
+        pending_rest = pi & 1;
+      }
     }
   }
+  if (pending_rest >= 0) CUDA_TRY(cudaStreamWaitEvent(st, c->sev[1 + pending_rest], 0));
   scale_rhs_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->sol, c->dinv, n);
   launches++;
   const int npan = (n + NB - 1) / NB;
-  for (int pi = npan - 1; pi >= 0; pi--) {
-    const int j0 = pi * NB;
-    const int nbw = (n - j0 < NB) ? n - j0 : NB;
-    const int blocks = j0 > 0 ? (j0 + 31) / 32 : 1;
-    ldl_back_kernel<<<blocks, 256, 0, st>>>(c->A, n, j0, nbw, c->Xinv + (size_t)pi * NB * NB, c->sol, c->dx);
+  for (int hi = npan - 1; hi >= 0; hi -= BACK_GROUP) {
+    const int lo = hi - BACK_GROUP + 1 > 0 ? hi - BACK_GROUP + 1 : 0;
+    const int g_lo = lo * NB;
+    const int g_hi = (hi + 1) * NB < n ? (hi + 1) * NB : n;
+    const int blocks = g_lo > 0 ? (g_lo + 31) / 32 : 1;
+    ldl_back_kernel<<<blocks, 256, 0, st>>>(c->A, n, g_lo, g_hi - g_lo, c->Xinv + (size_t)lo * NB * NB, c->sol, c->dx);
     launches++;
   }
   q1_kernel<<<1, 1024, 0, st>>>(c->dx, c->g, c->dvec, n, c->scal + 3, c->scal);
@@ -512,6 +566,7 @@ int launch_ldlt_solve(balm_ctx *c, double u) {
     CUDA_TRY(cudaMalloc((void **)&c->Xinv, sizeof(double) * (size_t)npan * NB * NB));
     CUDA_TRY(cudaMalloc((void **)&c->dinv, sizeof(double) * n));
     CUDA_TRY(cudaMalloc((void **)&c->sol, sizeof(double) * n));
+    c->solve_lookahead = getenv("BALM_NO_LOOKAHEAD") == nullptr;
   }
   c->h_scal[3] = u;  // pinned; the kernels read the damping factor from device memory so the graph is reusable
   CUDA_TRY(cudaMemcpyAsync(c->scal + 3, c->h_scal + 3, sizeof(double), cudaMemcpyHostToDevice, c->stream));
