@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
   double acc[BALM_ACC];
 #pragma unroll
   for (int q = 0; q < BALM_ACC; q++) acc[q] = 0.0;
-  double cmax[6] = {0, 0, 0, 0, 0, 0};
+  unsigned cmax[6] = {0, 0, 0, 0, 0, 0};  // high words of max|G'_j| (non-negative doubles order like their bit patterns)
   double scl[6] = {0, 0, 0, 0, 0, 0};
   const int S = EMIT ? *a.S_dev : 0;
   if (EMIT && active) {
@@ -193,25 +193,41 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
     }
   };
   issue(t0, onext);
+  // dense scenes: the voxel is warp-uniform, so its 20 stats words are fetched ONE ITERATION AHEAD by lanes 0..19
+  // (one word each), parked in a per-warp shared-memory slot at the top of the iteration and read back as
+  // broadcasts -- instead of ten L2-latency loads whose result is needed immediately
+  __shared__ __align__(16) double s_stats[4][2][BALM_STATS_STRIDE];
+  double st_next = 0.0;
+  if (DENSE && lane < BALM_STATS_STRIDE && t0 < t1) st_next = __ldg(a.stats + (t0 - a.v0) * BALM_STATS_STRIDE + lane);
   for (long long t = t0; t < t1; t++) {
     long long v;
     double o[10];
 #pragma unroll
     for (int c = 0; c < 10; c++) o[c] = onext[c];
     issue(t + 1, onext);
+    double st[BALM_STATS_STRIDE];
     if (DENSE) {
       v = t;
+      double *slot = s_stats[warp][(int)(t & 1)];
+      if (lane < BALM_STATS_STRIDE) slot[lane] = st_next;
+      __syncwarp();
+      if (lane < BALM_STATS_STRIDE && t + 1 < t1) st_next = __ldg(a.stats + (t + 1 - a.v0) * BALM_STATS_STRIDE + lane);
+#pragma unroll
+      for (int c = 0; c < BALM_STATS_STRIDE / 2; c++) {
+        const double2 x = reinterpret_cast<const double2 *>(slot)[c];
+        st[2 * c] = x.x;
+        st[2 * c + 1] = x.y;
+      }
       if (!active) continue;
     } else {
       v = a.csc_vox[t];
-    }
-    const double2 *st2 = reinterpret_cast<const double2 *>(a.stats + (v - a.v0) * BALM_STATS_STRIDE);
-    double st[BALM_STATS_STRIDE];
+      const double2 *st2 = reinterpret_cast<const double2 *>(a.stats + (v - a.v0) * BALM_STATS_STRIDE);
 #pragma unroll
-    for (int c = 0; c < BALM_STATS_STRIDE / 2; c++) {
-      const double2 x = __ldg(st2 + c);
-      st[2 * c] = x.x;
-      st[2 * c + 1] = x.y;
+      for (int c = 0; c < BALM_STATS_STRIDE / 2; c++) {
+        const double2 x = __ldg(st2 + c);
+        st[2 * c] = x.x;
+        st[2 * c + 1] = x.y;
+      }
     }
     const WC w = world_cluster(o, r, p);
     const double *vb = st, *u0 = st + 3, *u1 = st + 6, *u2 = st + 9;
@@ -271,8 +287,8 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
         for (int rr = 0; rr < 3; rr++) {
           unsigned D[6];
 #pragma unroll
-          for (int q = 0; q < 6; q++)
-            D[q] = ((unsigned)__double2int_rn(gv[rr][q] * scl[q]) + 0x80808080u) ^ 0x80808080u;
+          for (int q = 0; q < 6; q++)  // rint(G' sc) as the low word of G' sc + 1.5*2^52 (one DFMA, no conversion)
+            D[q] = ((unsigned)__double2loint(fma(gv[rr][q], scl[q], 6755399441055744.0)) + 0x80808080u) ^ 0x80808080u;
           int8_t *base = a.Gq + (size_t)(3 * (v - a.v0) + rr) * a.ldg + 6 * i;
 #pragma unroll
           for (int kb = 0; kb < 4; kb++) {        // byte kb = digit of weight 256^kb = plane S-1-kb
@@ -288,7 +304,10 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
       if (MODE != OBS_INT8) {
 #pragma unroll
         for (int q = 0; q < 6; q++) {
-          cmax[q] = fmax(cmax[q], fmax(fabs(gv[0][q]), fmax(fabs(gv[1][q]), fabs(gv[2][q]))));
+          // column maximum on the integer pipe: compare the high words (the low word is accounted for by the +1 below)
+          cmax[q] = max(max(cmax[q], (unsigned)__double2hiint(gv[0][q]) & 0x7fffffffu),
+                        max((unsigned)__double2hiint(gv[1][q]) & 0x7fffffffu,
+                            (unsigned)__double2hiint(gv[2][q]) & 0x7fffffffu));
           // exact diagonal of G'^T G': the split-integer SYRK drops the digit pair (S/2,S/2), which is a positive
           // bias on sums of squares only -- the n diagonal entries are therefore taken from this fp64 sum instead
           acc[27 + q] += gv[0][q] * gv[0][q] + gv[1][q] * gv[1][q] + gv[2][q] * gv[2][q];
@@ -340,8 +359,8 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
   }
   if (MODE != OBS_INT8 && active && a.colmax) {
 #pragma unroll
-    for (int q = 0; q < 6; q++)  // non-negative doubles order like their bit patterns
-      atomicMax(a.colmax + 6 * i + q, (unsigned long long)__double_as_longlong(cmax[q]));
+    for (int q = 0; q < 6; q++)  // upper bound of the maximum, tight to 2^-20: next high word, low word zero
+      if (cmax[q]) atomicMax(a.colmax + 6 * i + q, (unsigned long long)(cmax[q] + 1u) << 32);
   }
   if (MODE != OBS_INT8 && active) {
     double *pp = a.part + (size_t)blockIdx.x * BALM_ACC * a.Np + i;
