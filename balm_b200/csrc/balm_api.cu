@@ -9,6 +9,7 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#include <time.h>
 #include "internal.cuh"
 
 void synth_host_poses(int N, uint64_t seed, double *poses_gt, double *poses_init);
@@ -69,6 +70,15 @@ static void free_problem(balm_ctx *c) {
 }
 
 static int alloc_problem_arrays(balm_ctx *c, int64_t M, int64_t K, bool with_fix) {
+  // A window of the same shape as the previous one (the common case when BA runs scan after scan, and what every
+  // repetition of a benchmark does) keeps every device buffer: cudaFree/cudaMalloc of several GB cost milliseconds.
+  c->reuse_ws = c->obs && c->stats && c->M == M && c->K == K && (c->fix != nullptr) == with_fix &&
+                !getenv("BALM_NO_BUFFER_REUSE");
+  if (c->reuse_ws) {
+    cudaFree(c->csc_ptr); cudaFree(c->csc_obs); cudaFree(c->csc_vox);
+    c->csc_ptr = c->csc_obs = c->csc_vox = nullptr;
+    return BALM_OK;
+  }
   free_problem(c);
   c->M = M; c->K = K;
   c->Kp = (K + 31) / 32 * 32;
@@ -82,6 +92,15 @@ static int alloc_problem_arrays(balm_ctx *c, int64_t M, int64_t K, bool with_fix
 
 // Workspaces that depend on the registered problem (batch size, split counts).
 static int alloc_workspaces(balm_ctx *c) {
+  if (c->reuse_ws) {  // same shape: batch size, split counts, tensor maps and digit-plane buffers are all unchanged
+    c->reuse_ws = false;
+    if (!c->dense && c->VB < c->M) {
+      balm_set_error("sparse co-visibility problems must fit one evaluation batch");
+      return BALM_ERR_UNSUPPORTED;
+    }
+    tensor_syrk_new_problem(c);
+    return BALM_OK;
+  }
   size_t g_budget = (size_t)16 << 30;  // bytes for the fp64 G' batch
   if (const char *e = getenv("BALM_G_BUDGET_MB")) g_budget = (size_t)atoll(e) << 20;  // tests: force batching
   int64_t vb = (int64_t)(g_budget / ((size_t)3 * c->ldg * sizeof(double)));
@@ -253,6 +272,7 @@ static int finish_registration(balm_ctx *c) {
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   cudaFree(d_out); cudaFree(d_planes);
   if (h_out[0]) {
+    free_problem(c);  // leave the context without a problem rather than with a malformed one
     balm_set_error("balm_set_voxels: pose_idx must be ascending and in [0,N) inside each voxel");
     return BALM_ERR_INVALID;
   }
@@ -320,8 +340,16 @@ static int upload_aos(balm_ctx *c, const double *aos, bool aos_on_device, double
   return BALM_OK;
 }
 
+static double host_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec;
+}
+
 extern "C" int balm_set_voxels(balm_ctx *c, int64_t M, const int64_t *row_ptr, const int32_t *pose_idx,
                                const double *obs10, const double *fix10, const double *coe) {
+  const bool trace = getenv("BALM_TRACE_REG") != nullptr;  // host-side stage times of the registration
+  const double t_begin = host_ms();
   if (!c || M < 1 || !row_ptr || !pose_idx || !obs10 || !coe) {
     balm_set_error("balm_set_voxels: bad arguments");
     return BALM_ERR_INVALID;
@@ -331,12 +359,22 @@ extern "C" int balm_set_voxels(balm_ctx *c, int64_t M, const int64_t *row_ptr, c
   if (row_ptr[0] != 0 || K < M) { balm_set_error("balm_set_voxels: bad row_ptr"); return BALM_ERR_INVALID; }
   if (K >= ((int64_t)1 << 31)) { balm_set_error("balm_set_voxels: more than 2^31 observations per GPU"); return BALM_ERR_UNSUPPORTED; }
   TRY(alloc_problem_arrays(c, M, K, fix10 != nullptr));
+  const bool reused = c->reuse_ws;
+  const double t_alloc = host_ms();
   CUDA_TRY(cudaMemcpyAsync(c->row_ptr, row_ptr, sizeof(int64_t) * (M + 1), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->pose_idx, pose_idx, sizeof(int32_t) * K, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->coe, coe, sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
+  if (trace) CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const double t_small = host_ms();
   TRY(upload_aos(c, obs10, false, c->obs, K, c->Kp));
   if (fix10) TRY(upload_aos(c, fix10, false, c->fix, M, M));
-  return finish_registration(c);
+  const double t_obs = host_ms();
+  const int rc = finish_registration(c);
+  if (trace)
+    fprintf(stderr, "[balm_set_voxels] reuse=%d alloc %.2f ms, csr+coe copies %.2f ms, observations %.2f ms, "
+            "checks+workspaces %.2f ms\n", (int)reused, t_alloc - t_begin, t_small - t_alloc, t_obs - t_small,
+            host_ms() - t_obs);
+  return rc;
 }
 
 extern "C" int balm_set_voxels_dev(balm_ctx *c, int64_t M, const int64_t *row_ptr_dev, const int32_t *pose_idx_dev,
@@ -448,6 +486,10 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
   CUDA_TRY(cudaMemsetAsync(r_dev, 0, sizeof(double), c->stream));
   float ms;
   bool first = true;
+  // defer mode (LM loop, whole problem in one batch): nothing is waited for here; collect_eval() reads the events and
+  // the tensor path's flags after the iteration's single synchronisation
+  const bool deferred = c->defer && head == 0 && end == c->M && c->VB >= c->M && end > head;
+  c->pending_stats_cached = stats_cached;
   if (head == end) {  // empty range: H = 0
     CUDA_TRY(cudaMemsetAsync(c->H, 0, sizeof(double) * ((size_t)c->n * c->n + c->n + 1), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->scal, 0, sizeof(double), c->stream));
@@ -467,12 +509,16 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
       TRY(launch_syrk_f64(c, 3 * (v1 - v0), first));
     }
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-    CUDA_TRY(cudaEventSynchronize(c->ev[3]));
-    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-    if (!stats_cached) { c->tm.ms_stats += ms; if (first) c->tm.n_stats += 1; }
-    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->tm.ms_obs += ms;
-    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->tm.ms_syrk += ms;
-    if (c->prec == BALM_PREC_TENSOR) TRY(tensor_syrk_check(c));
+    if (deferred) {
+      if (c->prec == BALM_PREC_TENSOR) TRY(tensor_syrk_check_enqueue(c));
+    } else {
+      CUDA_TRY(cudaEventSynchronize(c->ev[3]));
+      cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+      if (!stats_cached) { c->tm.ms_stats += ms; if (first) c->tm.n_stats += 1; }
+      cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->tm.ms_obs += ms;
+      cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->tm.ms_syrk += ms;
+      if (c->prec == BALM_PREC_TENSOR) TRY(tensor_syrk_check(c));
+    }
     first = false;
   }
   CUDA_TRY(cudaMemcpyAsync(c->scal + BALM_SCAL_RCUR, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // local, pre all-reduce
@@ -482,10 +528,30 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
   TRY(allreduce_sum(c, c->H, (size_t)c->n * c->n + c->n + 1));
   CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->scal, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (deferred) {
+    c->pending_eval = true;
+    return BALM_OK;
+  }
   CUDA_TRY(cudaEventSynchronize(c->ev[6]));
   cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->tm.ms_assemble += ms;
   cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); c->tm.ms_allreduce += ms;
   c->tm.n_eval += 1;
+  return BALM_OK;
+}
+
+// defer mode: the stream has been synchronised -> account the evaluation's phases, read the tensor path's flags
+static int collect_eval(balm_ctx *c) {
+  if (!c->pending_eval) return BALM_OK;
+  c->pending_eval = false;
+  float ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  if (!c->pending_stats_cached) { c->tm.ms_stats += ms; c->tm.n_stats += 1; }
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->tm.ms_obs += ms;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->tm.ms_syrk += ms;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->tm.ms_assemble += ms;
+  cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); c->tm.ms_allreduce += ms;
+  c->tm.n_eval += 1;
+  if (c->prec == BALM_PREC_TENSOR) return tensor_syrk_check_finish(c);
   return BALM_OK;
 }
 
@@ -530,13 +596,7 @@ extern "C" int balm_residual(balm_ctx *c, const double *poses12, double *residua
   return residual_dev(c, c->poses_trial, residual);
 }
 
-static int solve_dev(balm_ctx *c, double u, double *q1, int *not_pd) {
-  CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
-  TRY(launch_ldlt_solve(c, u));
-  CUDA_TRY(cudaEventRecord(c->ev[10], c->stream));
-  CUDA_TRY(cudaMemcpyAsync(c->h_scal + 1, c->scal + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+static int collect_solve(balm_ctx *c, double *q1, int *not_pd) {
   float ms;
   cudaEventElapsedTime(&ms, c->ev[9], c->ev[10]);
   c->tm.ms_solve += ms;
@@ -544,6 +604,17 @@ static int solve_dev(balm_ctx *c, double u, double *q1, int *not_pd) {
   *q1 = c->h_scal[1];
   *not_pd = c->h_flags[0] != 0 || !std::isfinite(*q1);
   return BALM_OK;
+}
+
+static int solve_dev(balm_ctx *c, double u, double *q1, int *not_pd) {
+  CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
+  TRY(launch_ldlt_solve(c, u));
+  CUDA_TRY(cudaEventRecord(c->ev[10], c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_scal + 1, c->scal + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (c->defer) return BALM_OK;  // collect_solve() after the iteration's synchronisation
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return collect_solve(c, q1, not_pd);
 }
 
 extern "C" int balm_solve(balm_ctx *c, double u, double *dx, double *q1, int *not_pd) {
@@ -589,17 +660,28 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
   const bool hand_over = c->stats_trial != nullptr && (c->fix == nullptr || o->hess_includes_fix != 0);
   bool stats_cached = false;
   for (int it = 0; it < o->max_iter; it++) {
+    // evaluation -> solve -> pose update -> trial residual are enqueued back to back; the host waits once, at the
+    // end of residual_dev, and then reads r1, q1, the pivot flag and the phase timers
+    c->defer = !getenv("BALM_SYNC_PHASES");
+    int rc = BALM_OK;
     if (calc_hess) {
-      TRY(evaluate_dev(c, c->poses, 0, c->M, o->hess_includes_fix != 0, stats_cached));
-      CUDA_TRY(cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      CUDA_TRY(cudaStreamSynchronize(c->stream));
-      r1 = c->h_scal[0];
+      rc = evaluate_dev(c, c->poses, 0, c->M, o->hess_includes_fix != 0, stats_cached);
+      if (rc == BALM_OK && cudaMemcpyAsync(c->h_scal, c->scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        rc = BALM_ERR_CUDA;
     }
     double q1 = 0;
     int not_pd = 0;
-    TRY(solve_dev(c, u, &q1, &not_pd));
-    TRY(launch_pose_update(c, c->poses, c->dx, c->poses_trial));
-    TRY(residual_dev(c, c->poses_trial, &r2, hand_over));
+    if (rc == BALM_OK) rc = solve_dev(c, u, &q1, &not_pd);
+    if (rc == BALM_OK) rc = launch_pose_update(c, c->poses, c->dx, c->poses_trial);
+    if (rc == BALM_OK) rc = residual_dev(c, c->poses_trial, &r2, hand_over);  // synchronises the stream
+    const bool was_deferred = c->defer;
+    c->defer = false;
+    if (rc != BALM_OK) { c->pending_eval = false; return rc; }
+    if (was_deferred) {
+      TRY(collect_eval(c));
+      TRY(collect_solve(c, &q1, &not_pd));
+    }
+    if (calc_hess) r1 = c->h_scal[0];
     double q = r1 - r2;
     if (not_pd || !std::isfinite(r2)) q = -1.0;  // unusable step -> rejected, u *= v
     if (o->verbose)  // the reference's trace line (bavoxel.hpp:1132)

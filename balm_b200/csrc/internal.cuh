@@ -34,6 +34,10 @@ struct balm_ctx {
   cudaStream_t stream2 = nullptr;  // side stream of the solve's look-ahead (lower priority)
   cudaEvent_t sev[3] = {nullptr, nullptr, nullptr};  // panel done / rest done (two parities)
   bool solve_lookahead = true;
+  bool reuse_ws = false;      // the registration in progress has the shape of the previous one: buffers are kept
+  bool defer = false;         // inside balm_damping_iter: phases are enqueued back to back, one host sync per iteration
+  bool pending_eval = false;  // an evaluation's events / flags still have to be read (defer mode)
+  bool pending_stats_cached = false;
   int sm_count = 148;
 
   // ---- registered problem (device) ----
@@ -265,3 +269,6 @@ int ldlt_setup();
 int tensor_syrk_init(balm_ctx *c);
 void tensor_syrk_free(balm_ctx *c);
 int tensor_syrk_check(balm_ctx *c);
+int tensor_syrk_check_enqueue(balm_ctx *c);
+int tensor_syrk_check_finish(balm_ctx *c);
+void tensor_syrk_new_problem(balm_ctx *c);

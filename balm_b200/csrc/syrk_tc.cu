@@ -987,20 +987,38 @@ int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1
   return BALM_OK;
 }
 
-int tensor_syrk_check(balm_ctx *c) {
+// The SYRK's error flag, the digit-plane count and the speculation verdict of the batch in flight: the copies are
+// enqueued (pinned host words), the host reads them after its next synchronisation of the stream.
+int tensor_syrk_check_enqueue(balm_ctx *c) {
   TcState *st = static_cast<TcState *>(c->tmap);
   if (!st) return BALM_OK;
-  int e = 0;
-  CUDA_TRY(cudaMemcpyAsync(&e, st->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  int ok = 0;
-  CUDA_TRY(cudaMemcpyAsync(&st->last_S, st->S_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaMemcpyAsync(&ok, st->spec_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_flags + 1, st->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_flags + 2, st->S_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->h_flags + 3, st->spec_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  return BALM_OK;
+}
+
+int tensor_syrk_check_finish(balm_ctx *c) {  // after the stream has been synchronised
+  TcState *st = static_cast<TcState *>(c->tmap);
+  if (!st) return BALM_OK;
+  st->last_S = c->h_flags[2];
   c->tm.digit_planes = st->last_S;
-  if (st->last_spec) (ok ? c->tm.single_sweeps : c->tm.redone_sweeps) += 1;
-  if (e != 0) {
+  if (st->last_spec) (c->h_flags[3] ? c->tm.single_sweeps : c->tm.redone_sweeps) += 1;
+  if (c->h_flags[1] != 0) {
     balm_set_error("tcgen05 SYRK pipeline timed out (mbarrier wait bound exceeded)");
     return BALM_ERR_CUDA;
   }
   return BALM_OK;
+}
+
+int tensor_syrk_check(balm_ctx *c) {
+  int rc = tensor_syrk_check_enqueue(c);
+  if (rc != BALM_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return tensor_syrk_check_finish(c);
+}
+
+void tensor_syrk_new_problem(balm_ctx *c) {  // same-shape re-registration: the workspaces stay, the speculation does not
+  TcState *st = static_cast<TcState *>(c->tmap);
+  if (st) st->spec_ready = false;
 }

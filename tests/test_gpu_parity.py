@@ -98,6 +98,58 @@ def test_tensor_single_sweep_speculation(drop):
     assert c.timings()["redone_sweeps"] >= 2
 
 
+@pytest.mark.parametrize("prec", PRECS)
+def test_reregistration_same_shape_reuses_buffers(prec):
+    """A second window of the same shape keeps the device buffers (no free/malloc) -- results must be those of a
+    fresh context, and nothing speculative may leak from the previous problem."""
+    import balm_b200
+    from balm_b200 import _lib
+    scA = scenes.make_scene(n_poses=16, n_planes=90, seed=41)
+    scB = scenes.make_scene(n_poses=16, n_planes=90, seed=42)
+    c = _ctx(scA, prec)
+    c.evaluate(scA["poses_init"])
+    c.damping_iter(scA["poses_init"], max_iter=3)
+    c.set_voxels(scB["row_ptr"], scB["pose_idx"], scB["obs10"], scB["coe"], scB["fix10"])
+    c.reset_counters()
+    o = _oracle(scB)
+    H, g, r = _check_eval(c, o, scB["poses_init"], tolH=TOLH[prec])
+    assert c.timings()["single_sweeps"] == 0                      # first evaluation of a new problem sweeps twice
+    fresh = _ctx(scB, prec)
+    H2, g2, r2 = fresh.evaluate(scB["poses_init"])
+    assert np.array_equal(H, H2) and np.array_equal(g, g2) and r == r2
+    pa, ta, _ = c.damping_iter(scB["poses_init"], max_iter=4)
+    pb, tb, _ = fresh.damping_iter(scB["poses_init"], max_iter=4)
+    assert [t["accepted"] for t in ta] == [t["accepted"] for t in tb]
+    assert np.abs(pa - pb).max() <= 1e-9
+    # a malformed registration leaves the context empty, not half-registered
+    bad = scB["pose_idx"].copy()
+    bad[1] = bad[0]
+    with pytest.raises(_lib.BalmError):
+        c.set_voxels(scB["row_ptr"], bad, scB["obs10"], scB["coe"], scB["fix10"])
+    with pytest.raises(_lib.BalmError):
+        c.evaluate(scB["poses_init"])
+    c.set_voxels(scB["row_ptr"], scB["pose_idx"], scB["obs10"], scB["coe"], scB["fix10"])
+    H3, g3, r3 = c.evaluate(scB["poses_init"])
+    assert np.array_equal(H3, H2)
+
+
+def test_phase_pipelining_gives_identical_results(monkeypatch):
+    """The LM loop enqueues evaluation, solve, update and trial residual back to back (one host wait per iteration);
+    BALM_SYNC_PHASES=1 waits after every phase. Same kernels, same order -> bit-identical poses and trace."""
+    sc = scenes.make_scene(n_poses=20, n_planes=120, seed=44, drop=0.3)
+    res = []
+    for flag in (None, "1"):
+        if flag:
+            monkeypatch.setenv("BALM_SYNC_PHASES", flag)
+        c = _ctx(sc, 1)
+        poses, tr, _ = c.damping_iter(sc["poses_init"], max_iter=5)
+        tm = c.timings()
+        assert tm["n_eval"] >= 1 and tm["n_solve"] == len(tr) and tm["n_residual"] == len(tr)
+        assert tm["ms_solve"] > 0 and tm["ms_syrk"] > 0
+        res.append((poses, [(t["r1"], t["r2"], t["q1"], t["accepted"]) for t in tr]))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+
+
 def test_voxel_range_semantics():
     sc = scenes.make_scene(n_poses=10, n_planes=60, seed=22)
     c, o = _ctx(sc), _oracle(sc)
