@@ -9,7 +9,9 @@ from ._lib import PREC_FP64, PREC_TENSOR, BalmError
 from .context import Context
 from . import bavoxel
 from . import shard
+from . import io
+from . import drivers
 from .bavoxel import BALM2, IMUST, VOX_HESS, PointCluster
 
 __all__ = ["Context", "BALM2", "VOX_HESS", "IMUST", "PointCluster", "PREC_FP64", "PREC_TENSOR", "BalmError",
-           "bavoxel", "shard"]
+           "bavoxel", "shard", "io", "drivers"]
