@@ -34,6 +34,7 @@ struct balm_ctx {
   cudaStream_t stream2 = nullptr;  // side stream of the solve's look-ahead (lower priority)
   cudaEvent_t sev[3] = {nullptr, nullptr, nullptr};  // panel done / rest done (two parities)
   bool solve_lookahead = true;
+  double *ysol = nullptr;          // [n] forward-substitution result y (kept apart from the running rhs `sol`)
   bool reuse_ws = false;      // the registration in progress has the shape of the previous one: buffers are kept
   bool defer = false;         // inside balm_damping_iter: phases are enqueued back to back, one host sync per iteration
   bool pending_eval = false;  // an evaluation's events / flags still have to be read (defer mode)

@@ -47,34 +47,11 @@ __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
 // thread per row, its 16 panel entries in registers) with a 64-thread named barrier per column -- the serial chain
 // of the whole solve is n = 6N of these column steps, so each step is kept to: post column -> barrier -> reciprocal
 // -> <=15 FMAs. The rank-16 trailing update and the assembly of X = L11^-1 from 16x16 inverses use all 256 threads.
-__global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0, int nbw, double *Xcm, double *dinv_all,
-                                                       double *sol, int *flags) {
-  extern __shared__ double dyn_smem[];
-  double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);                   // the block (lower) -> L, d
-  double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));  // L11^-1
-  double (*Wp)[17] = reinterpret_cast<double (*)[17]>(dyn_smem + 2 * NB * (NB + 1));     // current sub-panel times d
-  double (*col16)[16] = reinterpret_cast<double (*)[16]>(dyn_smem + 2 * NB * (NB + 1) + NB * 17);
-  double *bvec = dyn_smem + 2 * NB * (NB + 1) + NB * 17 + 32;
+// In: S = the block (lower triangle), Xs = 0, all threads synchronised. Out: S = L (below the diagonal) and d (on
+// it), Xs = L11^-1 (lower), all threads synchronised. Returns true if a pivot was zero / non-finite.
+__device__ __forceinline__ bool diag_factor(double (*S)[NB + 1], double (*Xs)[NB + 1], double (*Wp)[17],
+                                            double (*col16)[16]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  {
-    double ld[16];  // all 16 global loads of this thread in flight together (the kernel is pure latency)
-#pragma unroll
-    for (int it = 0; it < 16; it++) {
-      const int e = tid + it * 256, r = e & (NB - 1), c = e >> 6;
-      double v = (r == c) ? 1.0 : 0.0;  // rows/cols of a short last panel act as identity
-      if (r < nbw && c < nbw && r >= c) v = A[(size_t)(j0 + c) * n + j0 + r];
-      ld[it] = v;
-    }
-    const double bv = (tid < nbw) ? sol[j0 + tid] : 0.0;
-#pragma unroll
-    for (int it = 0; it < 16; it++) {
-      const int e = tid + it * 256, r = e & (NB - 1), c = e >> 6;
-      S[r][c] = ld[it];
-      Xs[r][c] = 0.0;
-    }
-    if (tid < NB) bvec[tid] = bv;
-  }
-  __syncthreads();
   bool bad = false;
 #pragma unroll 1
   for (int cb = 0; cb < NB; cb += 16) {
@@ -127,7 +104,6 @@ __global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0,
     }
     __syncthreads();
   }
-  if (bad && tid == 0) atomicOr(&flags[0], 1);
 
   // ---- X = L11^-1: 16x16 diagonal-block inverses (one warp each, shuffles only) ----
   if (warp < 4) {
@@ -179,6 +155,42 @@ __global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0,
       if (cq < b) Xs[rb + ri][16 * cq + ci] = xn[cq];
     __syncthreads();
   }
+  return bad;
+}
+
+// Diagonal step: factor, write L11/d back, X, 1/d, y_j = X b_j (y goes to `ysol`; `sol` keeps the running rhs).
+// (Factoring the block redundantly inside every panel CTA, to drop this kernel boundary from the critical path, was
+// measured and is NOT faster: 2.81 vs 2.72 ms at n = 3000.)
+__global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0, int nbw, double *Xcm, double *dinv_all,
+                                                       const double *sol, double *ysol, int *flags) {
+  extern __shared__ double dyn_smem[];
+  double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);                   // the block (lower) -> L, d
+  double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));  // L11^-1
+  double (*Wp)[17] = reinterpret_cast<double (*)[17]>(dyn_smem + 2 * NB * (NB + 1));     // current sub-panel times d
+  double (*col16)[16] = reinterpret_cast<double (*)[16]>(dyn_smem + 2 * NB * (NB + 1) + NB * 17);
+  double *bvec = dyn_smem + 2 * NB * (NB + 1) + NB * 17 + 32;
+  const int tid = threadIdx.x;
+  {
+    double ld[16];  // all 16 global loads of this thread in flight together (the kernel is pure latency)
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+      const int e = tid + it * 256, r = e & (NB - 1), c = e >> 6;
+      double v = (r == c) ? 1.0 : 0.0;  // rows/cols of a short last panel act as identity
+      if (r < nbw && c < nbw && r >= c) v = A[(size_t)(j0 + c) * n + j0 + r];
+      ld[it] = v;
+    }
+    const double bv = (tid < nbw) ? sol[j0 + tid] : 0.0;
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+      const int e = tid + it * 256, r = e & (NB - 1), c = e >> 6;
+      S[r][c] = ld[it];
+      Xs[r][c] = 0.0;
+    }
+    if (tid < NB) bvec[tid] = bv;
+  }
+  __syncthreads();
+  const bool bad = diag_factor(S, Xs, Wp, col16);
+  if (bad && tid == 0) atomicOr(&flags[0], 1);
   // ---- write back L11 / d, X (column-major), 1/d, and y_j = X b_j ----
 #pragma unroll 4
   for (int e = tid; e < NB * NB; e += 256) {
@@ -190,12 +202,12 @@ __global__ void __launch_bounds__(256) ldl_diag_kernel(double *A, int n, int j0,
   if (tid < NB) {
     double sacc = 0.0;
     for (int c = 0; c <= tid; c++) sacc += Xs[tid][c] * bvec[c];
-    if (tid < nbw) sol[j0 + tid] = sacc;
+    if (tid < nbw) ysol[j0 + tid] = sacc;
   }
 }
 
 __global__ void __launch_bounds__(256) ldl_panel_kernel(double *A, double *W, int n, int j0, int nbw, const double *Xcm,
-                                                        const double *dinv_all, double *sol) {
+                                                        const double *dinv_all, double *sol, const double *ysol) {
   extern __shared__ double dyn_smem[];
   double (*sA)[NB + 4] = reinterpret_cast<double (*)[NB + 4]>(dyn_smem);                  // [k][row]
   double (*sX)[NB + 4] = reinterpret_cast<double (*)[NB + 4]>(dyn_smem + NB * (NB + 4));  // [k][col] = X[col][k]
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(256) ldl_panel_kernel(double *A, double *W, in
     }
   }
   if (tid < NB) {
-    yj[tid] = tid < nbw ? sol[j0 + tid] : 0.0;
+    yj[tid] = tid < nbw ? ysol[j0 + tid] : 0.0;
     dv[tid] = tid < nbw ? dinv_all[j0 + tid] : 0.0;
   }
   __syncthreads();
@@ -417,9 +429,9 @@ __global__ void __launch_bounds__(256) ldl_back_kernel(const double *A, int n, i
   }
 }
 
-__global__ void scale_rhs_kernel(double *sol, const double *dinv_all, int n) {
+__global__ void scale_rhs_kernel(double *sol, const double *ysol, const double *dinv_all, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) sol[i] *= dinv_all[i];
+  if (i < n) sol[i] = ysol[i] * dinv_all[i];  // w = d^-1 y: start of the backward substitution
 }
 
 __global__ void __launch_bounds__(1024) q1_kernel(const double *x, const double *g, const double *dvec, int n,
@@ -512,12 +524,12 @@ static int enqueue_solve(balm_ctx *c) {
     const int nbw = (n - j0 < NB) ? n - j0 : NB;
     double *X = c->Xinv + (size_t)pi * NB * NB;
     double *W = c->W + (size_t)(pi & 1) * n * NB;
-    ldl_diag_kernel<<<1, 256, DIAG_SMEM, st>>>(c->A, n, j0, nbw, X, c->dinv, c->sol, c->flags);
-    launches++;
     const int m = n - j0 - nbw;
+    const int mt = (m + NB - 1) / NB, mu = (m + UT - 1) / UT;
+    ldl_diag_kernel<<<1, 256, DIAG_SMEM, st>>>(c->A, n, j0, nbw, X, c->dinv, c->sol, c->ysol, c->flags);
+    launches++;
     if (m > 0) {
-      const int mt = (m + NB - 1) / NB, mu = (m + UT - 1) / UT;
-      ldl_panel_kernel<<<mt, 256, panel_smem, st>>>(c->A, W, n, j0, nbw, X, c->dinv, c->sol);
+      ldl_panel_kernel<<<mt, 256, panel_smem, st>>>(c->A, W, n, j0, nbw, X, c->dinv, c->sol, c->ysol);
       launches++;
       const int base = j0 + nbw;
       if (!c->solve_lookahead) {
@@ -542,7 +554,7 @@ static int enqueue_solve(balm_ctx *c) {
     }
   }
   if (pending_rest >= 0) CUDA_TRY(cudaStreamWaitEvent(st, c->sev[1 + pending_rest], 0));
-  scale_rhs_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->sol, c->dinv, n);
+  scale_rhs_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->sol, c->ysol, c->dinv, n);
   launches++;
   const int npan = (n + NB - 1) / NB;
   for (int hi = npan - 1; hi >= 0; hi -= BACK_GROUP) {
@@ -566,6 +578,7 @@ int launch_ldlt_solve(balm_ctx *c, double u) {
     CUDA_TRY(cudaMalloc((void **)&c->Xinv, sizeof(double) * (size_t)npan * NB * NB));
     CUDA_TRY(cudaMalloc((void **)&c->dinv, sizeof(double) * n));
     CUDA_TRY(cudaMalloc((void **)&c->sol, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc((void **)&c->ysol, sizeof(double) * n));
     c->solve_lookahead = getenv("BALM_NO_LOOKAHEAD") == nullptr;
   }
   c->h_scal[3] = u;  // pinned; the kernels read the damping factor from device memory so the graph is reusable
