@@ -659,6 +659,12 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
   // problem in one batch and the same treatment of the fix cluster in both passes.
   const bool hand_over = c->stats_trial != nullptr && (c->fix == nullptr || o->hess_includes_fix != 0);
   bool stats_cached = false;
+  tensor_syrk_new_problem(c);  // nothing speculative is carried over from earlier calls
+  struct LmScope {             // lm_active / defer are cleared on every exit path
+    balm_ctx *c;
+    ~LmScope() { c->lm_active = false; c->defer = false; c->pending_eval = false; }
+  } lm_scope{c};
+  c->lm_active = true;
   for (int it = 0; it < o->max_iter; it++) {
     // evaluation -> solve -> pose update -> trial residual are enqueued back to back; the host waits once, at the
     // end of residual_dev, and then reads r1, q1, the pivot flag and the phase timers

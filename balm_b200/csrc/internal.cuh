@@ -35,6 +35,7 @@ struct balm_ctx {
   cudaEvent_t sev[3] = {nullptr, nullptr, nullptr};  // panel done / rest done (two parities)
   bool solve_lookahead = true;
   double *ysol = nullptr;          // [n] forward-substitution result y (kept apart from the running rhs `sol`)
+  bool lm_active = false;     // inside balm_damping_iter (scale speculation and stats hand-over are loop-local)
   bool reuse_ws = false;      // the registration in progress has the shape of the previous one: buffers are kept
   bool defer = false;         // inside balm_damping_iter: phases are enqueued back to back, one host sync per iteration
   bool pending_eval = false;  // an evaluation's events / flags still have to be read (defer mode)

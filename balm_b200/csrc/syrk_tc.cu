@@ -761,12 +761,14 @@ __global__ void __launch_bounds__(1024) tc_scale_kernel(const unsigned long long
 }
 
 // start of a speculative evaluation: the scales found by the previous one become the ones in use
+// (skew: test hook BALM_TC_SPEC_SKEW -- the adopted scales are multiplied by 2^skew so that the device-side check
+//  has something to reject; 0 in production)
 __global__ void tc_adopt_kernel(double *sc, double *isc, int *S_dev, const double *sc_next, const double *isc_next,
-                                const int *S_next, int ldq) {
+                                const int *S_next, int ldq, int skew) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < ldq) {
-    sc[j] = sc_next[j];
-    isc[j] = isc_next[j];
+    sc[j] = ldexp(sc_next[j], skew);
+    isc[j] = ldexp(isc_next[j], -skew);
   }
   if (j == 0) *S_dev = *S_next;
 }
@@ -791,6 +793,7 @@ struct TcState {
   bool spec_ready = false;                         // sc_next/S_next describe the currently registered voxels
   bool spec_enabled = true;                        // BALM_NO_SPEC=1 keeps the two-sweep path
   bool last_spec = false;                          // the batch in flight used the fused sweep
+  int spec_skew = 0;                               // BALM_TC_SPEC_SKEW (tests)
   unsigned long long *colmax = nullptr;
   int *err = nullptr;
   int64_t rows_alloc = 0;
@@ -823,6 +826,7 @@ int tensor_syrk_init(balm_ctx *c) {
   CUDA_TRY(cudaMalloc((void **)&st->spec_ok, sizeof(int)));
   CUDA_TRY(cudaMemset(st->spec_ok, 0, sizeof(int)));
   st->spec_enabled = getenv("BALM_NO_SPEC") == nullptr;
+  if (const char *e = getenv("BALM_TC_SPEC_SKEW")) st->spec_skew = atoi(e);
   CUDA_TRY(cudaMalloc((void **)&st->colmax, sizeof(unsigned long long) * ldq));
   CUDA_TRY(cudaMalloc((void **)&st->err, sizeof(int)));
   CUDA_TRY(cudaMemset(st->err, 0, sizeof(int)));
@@ -932,13 +936,16 @@ int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1
   const int64_t rows = 3 * (v1 - v0);
   const int64_t rows_padded = (rows + KS - 1) / KS * KS;
   CUDA_TRY(cudaMemsetAsync(st->colmax, 0, sizeof(unsigned long long) * ldq, c->stream));
-  const bool full = (v0 == 0 && v1 == c->M);  // only full-range evaluations feed / use the speculation
+  // Speculation lives inside one balm_damping_iter call only: its first evaluation sweeps twice, and the public
+  // balm_evaluate always does -- so every entry point stays a pure function of its arguments (same inputs, same bits,
+  // whatever was evaluated before).
+  const bool full = c->lm_active && v0 == 0 && v1 == c->M;
   const bool spec = full && st->spec_ready && st->spec_enabled;
   const int64_t plane_stride = (int64_t)st->rows_alloc * ldq;
   int rc;
   if (spec) {  // one sweep with the previous evaluation's scales; sweep 2 below only runs if tc_scale_kernel re-arms it
     tc_adopt_kernel<<<(ldq + 255) / 256, 256, 0, c->stream>>>(st->sc, st->isc, st->S_dev, st->sc_next, st->isc_next,
-                                                              st->S_next, ldq);
+                                                              st->S_next, ldq, st->spec_skew);
     c->launches += 1;
     rc = launch_obs_int8(c, poses, v0, v1, first_batch, st->sc, c->Gq, plane_stride, st->S_dev, SMAX, rows_padded, true,
                          nullptr);

@@ -69,33 +69,43 @@ def test_evaluate_matches_oracle(n_poses, n_planes, drop, with_fix, prec):
 
 
 @pytest.mark.parametrize("drop", [0.0, 0.4])
-def test_tensor_single_sweep_speculation(drop):
-    """Tensor path: from the second full evaluation on, the column scales come from the previous evaluation and ONE
-    observation sweep writes the digit planes; the device-side check either accepts it or re-runs the digit sweep."""
+def test_tensor_single_sweep_speculation(drop, monkeypatch):
+    """Tensor path inside balm_damping_iter: from the second evaluation on, the column scales come from the previous
+    evaluation and ONE observation sweep writes the digit planes; a device-side check either accepts that or re-runs
+    the digit sweep with fresh scales. The public evaluate never speculates (pure function of its arguments)."""
     sc = scenes.make_scene(n_poses=24, n_planes=150, seed=33, drop=drop)
-    c, o = _ctx(sc, 1), _oracle(sc)
-    c.reset_counters()
-    H0, g0, r0 = _check_eval(c, o, sc["poses_init"], tolH=TOLH[1])            # two sweeps (nothing to speculate from)
-    tm = c.timings()
-    assert tm["single_sweeps"] == 0 and tm["redone_sweeps"] == 0
-    H1, g1, r1 = _check_eval(c, o, sc["poses_init"], tolH=TOLH[1])            # same poses -> same scales, accepted
-    tm = c.timings()
-    assert tm["single_sweeps"] == 1 and tm["redone_sweeps"] == 0
-    assert np.array_equal(H0, H1) and np.array_equal(g0, g1) and r0 == r1
-    rng = np.random.default_rng(3)
-    near = sc["poses_init"].copy()
-    near[:, 9:] += rng.normal(0, 1e-3, (len(near), 3))                        # an LM-step-sized move
-    _check_eval(c, o, near, tolH=TOLH[1])
-    tm = c.timings()
-    assert tm["single_sweeps"] + tm["redone_sweeps"] == 2
-    far = sc["poses_init"].copy()
-    far[:, 9:] *= 40.0                                                         # column maxima grow far beyond the 2x headroom
-    far[:, 9:] += 25.0
-    _check_eval(c, o, far, tolH=TOLH[1], tolr=1e-10)
-    tm = c.timings()
-    assert tm["redone_sweeps"] >= 1 and tm["single_sweeps"] + tm["redone_sweeps"] == 3
-    _check_eval(c, o, sc["poses_init"], tolH=TOLH[1])                          # and back: scales shrink by the same factor
-    assert c.timings()["redone_sweeps"] >= 2
+    kw = dict(max_iter=5, force_hess=True, rel_tol=-1.0)
+
+    def run():
+        c = _ctx(sc, 1)
+        c.reset_counters()
+        H0, g0, r0 = c.evaluate(sc["poses_init"])
+        H1, g1, r1 = c.evaluate(sc["poses_init"])
+        tm = c.timings()
+        assert tm["single_sweeps"] == 0 and tm["redone_sweeps"] == 0
+        assert np.array_equal(H0, H1) and np.array_equal(g0, g1) and r0 == r1
+        c.reset_counters()
+        poses, tr, _ = c.damping_iter(sc["poses_init"], **kw)
+        return poses, [(t["r1"], t["r2"], t["accepted"]) for t in tr], c.timings()
+
+    monkeypatch.setenv("BALM_NO_SPEC", "1")
+    p_two, t_two, tm = run()                                   # every evaluation sweeps twice
+    assert tm["n_eval"] == 5 and tm["single_sweeps"] == 0 and tm["redone_sweeps"] == 0
+    monkeypatch.delenv("BALM_NO_SPEC")
+    p_one, t_one, tm = run()
+    assert tm["n_eval"] == 5 and tm["single_sweeps"] + tm["redone_sweeps"] == 4 and tm["single_sweeps"] >= 1
+    assert [x[2] for x in t_one] == [x[2] for x in t_two]
+    rot, tra = _pose_err(p_one, p_two)
+    assert rot <= 1e-8 and tra <= 1e-8                         # scales differ by powers of two at most -> rounding only
+    for skew in (4, -9):   # adopted scales 16x too large (digits overflow) / 512x too small (precision lost)
+        monkeypatch.setenv("BALM_TC_SPEC_SKEW", str(skew))
+        p_bad, t_bad, tm = run()
+        assert tm["single_sweeps"] == 0 and tm["redone_sweeps"] == 4, (skew, tm)
+        # every speculation rejected -> the digit sweep re-ran with fresh scales -> the two-sweep result (the
+        # accumulators come from a different instantiation of the sweep kernel, hence "to rounding", not "same bits")
+        assert np.abs(p_bad - p_two).max() <= 1e-12
+        assert [x[2] for x in t_bad] == [x[2] for x in t_two]
+        assert max(abs(a[1] - b[1]) / abs(b[1]) for a, b in zip(t_bad, t_two)) <= 1e-12
 
 
 @pytest.mark.parametrize("prec", PRECS)
