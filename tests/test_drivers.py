@@ -38,10 +38,6 @@ def test_benchmark_realworld_from_files(tmp_path, capsys):
     assert np.abs(ref - res["poses"]).max() < 1e-9 and len(tr) == len(res["trace"])
     assert res["trace"][-1]["r2"] < res["trace"][0]["r1"]           # the cost went down
     assert np.abs(res["poses"][0] - np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0])).max() < 1e-12  # gauge: pose 0
-    # the poses moved towards the scans' true trajectory (known up to the common anchor)
-    gt = scenes.pack_poses([poses[0][0].T @ r for r, _ in poses], [poses[0][0].T @ (t - poses[0][1]) for _, t in poses])
-    # `poses` holds the NOISY initial guess; synthetic_scans built the scans from the noise-free trajectory
-    assert res["poses"].shape == gt.shape
 
 
 def test_benchmark_realworld_plane_guard(tmp_path, capsys):
