@@ -63,6 +63,7 @@ static void free_problem(balm_ctx *c) {
   cudaFree(c->csc_ptr); cudaFree(c->csc_obs); cudaFree(c->csc_vox);
   c->obs = nullptr; c->pose_idx = nullptr; c->row_ptr = nullptr; c->coe = nullptr; c->fix = nullptr;
   c->csc_ptr = c->csc_obs = c->csc_vox = nullptr;
+  cudaFree(c->vsums); c->vsums = nullptr;
   cudaFree(c->stats); cudaFree(c->stats_trial); cudaFree(c->G); cudaFree(c->obs_part); cudaFree(c->syrk_part);
   c->stats = c->stats_trial = c->G = c->obs_part = c->syrk_part = nullptr;
   tensor_syrk_free(c);
@@ -113,6 +114,7 @@ static int alloc_workspaces(balm_ctx *c) {
   c->VB = vb;
   TRY(dev_alloc(&c->stats, (size_t)vb * BALM_STATS_STRIDE));
   if (vb == c->M && !getenv("BALM_NO_STATS_CACHE")) TRY(dev_alloc(&c->stats_trial, (size_t)vb * BALM_STATS_STRIDE));
+  if (!getenv("BALM_NO_STATS_SPLIT")) TRY(dev_alloc(&c->vsums, (size_t)vb * 10));
   if (c->prec == BALM_PREC_FP64) {  // the tensor path writes int8 digit planes directly and never stores fp64 G'
     TRY(dev_alloc(&c->G, (size_t)3 * vb * c->ldg));
     CUDA_TRY(cudaMemsetAsync(c->G, 0, sizeof(double) * (size_t)3 * vb * c->ldg, c->stream));  // zero the column padding

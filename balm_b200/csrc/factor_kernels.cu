@@ -104,6 +104,102 @@ __global__ void __launch_bounds__(STATS_THREADS, 3) voxel_stats_kernel(StatsArgs
   if (lane == 0) a.res_part[gw] = res_acc;
 }
 
+// ---- the default form of the stats / residual pass: the streaming half and the eigen half as two kernels ----
+// (BALM_NO_STATS_SPLIT=1 selects the single voxel_stats_kernel above; measured at C3: 0.916 -> 0.831 ms)
+// voxel_sums_kernel: the same warp-per-voxel stream as above, but the warp only reduces the ten cluster sums and
+// moves on -- no serial eigen-solve between two voxels' loads. voxel_eig_kernel: one THREAD per voxel does the
+// eigen-solve (M independent chains instead of M x 32 redundant ones), the residual term and the stats record.
+template <bool SMEM_POSES>
+__global__ void __launch_bounds__(STATS_THREADS, 3) voxel_sums_kernel(StatsArgs a, double *sums /*[v1-v0][10]*/) {
+  extern __shared__ double s_poses[];
+  if (SMEM_POSES) {
+    for (int e = threadIdx.x; e < 12 * a.N; e += STATS_THREADS) s_poses[e] = a.poses[e];
+    __syncthreads();
+  }
+  const double *ptab = SMEM_POSES ? s_poses : a.poses;
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * STATS_WARPS + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * STATS_WARPS;
+  for (int64_t v = a.v0 + gw; v < a.v1; v += nw) {
+    const long long s0 = a.row_ptr[v];
+    const int k = (int)(a.row_ptr[v + 1] - s0);
+    double acc[10];
+#pragma unroll
+    for (int c = 0; c < 10; c++) acc[c] = 0.0;
+    for (int j = lane; j < k; j += 64) {
+      const long long sA = s0 + j;
+      const bool hasB = j + 32 < k;
+      const long long sB = hasB ? sA + 32 : sA;
+      double oa[10], ob[10];
+#pragma unroll
+      for (int c = 0; c < 10; c++) { oa[c] = ld_stream(a.obs + c * a.Kp + sA); ob[c] = ld_stream(a.obs + c * a.Kp + sB); }
+      const int pa = __ldg(a.pose_idx + sA), pb = __ldg(a.pose_idx + sB);
+      double r[9], p[3];
+      load_pose_any<SMEM_POSES>(ptab + 12 * pa, r, p);
+      WC w = world_cluster(oa, r, p);
+      acc[0] += w.p00; acc[1] += w.p01; acc[2] += w.p02; acc[3] += w.p11; acc[4] += w.p12;
+      acc[5] += w.p22; acc[6] += w.v0;  acc[7] += w.v1;  acc[8] += w.v2;  acc[9] += w.n;
+      if (hasB) {
+        load_pose_any<SMEM_POSES>(ptab + 12 * pb, r, p);
+        w = world_cluster(ob, r, p);
+        acc[0] += w.p00; acc[1] += w.p01; acc[2] += w.p02; acc[3] += w.p11; acc[4] += w.p12;
+        acc[5] += w.p22; acc[6] += w.v0;  acc[7] += w.v1;  acc[8] += w.v2;  acc[9] += w.n;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 10; c++) {
+      acc[c] = warp_sum(acc[c]);
+      if (a.fix) acc[c] += __ldg(a.fix + c * a.M + v);
+    }
+    double *dst = sums + (v - a.v0) * 10;
+#pragma unroll
+    for (int c = 0; c < 10; c++)
+      if (lane == c) dst[c] = acc[c];
+  }
+}
+
+template <bool STORE>
+__global__ void __launch_bounds__(128) voxel_eig_kernel(const double *sums, const double *coe_all, int64_t v0, int64_t v1,
+                                                        double *stats, double *res_part) {
+  __shared__ double red[4];
+  double res_acc = 0.0;
+  for (int64_t v = v0 + (int64_t)blockIdx.x * 128 + threadIdx.x; v < v1; v += (int64_t)gridDim.x * 128) {
+    const double2 *src = reinterpret_cast<const double2 *>(sums + (v - v0) * 10);
+    double acc[10];
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+      const double2 x = src[c];
+      acc[2 * c] = x.x;
+      acc[2 * c + 1] = x.y;
+    }
+    const double inv = 1.0 / acc[9];
+    const double vb0 = acc[6] * inv, vb1 = acc[7] * inv, vb2 = acc[8] * inv;
+    double lam[3], u0[3], u1[3], u2[3];
+    eig3_jacobi(acc[0] * inv - vb0 * vb0, acc[1] * inv - vb0 * vb1, acc[2] * inv - vb0 * vb2,
+                acc[3] * inv - vb1 * vb1, acc[4] * inv - vb1 * vb2, acc[5] * inv - vb2 * vb2, lam, u0, u1, u2);
+    const double coe = __ldg(coe_all + v);
+    res_acc += coe * lam[0];
+    if (STORE) {
+      double2 *st = reinterpret_cast<double2 *>(stats + (v - v0) * BALM_STATS_STRIDE);
+      st[0] = make_double2(vb0, vb1);
+      st[1] = make_double2(vb2, u0[0]);
+      st[2] = make_double2(u0[1], u0[2]);
+      st[3] = make_double2(u1[0], u1[1]);
+      st[4] = make_double2(u1[2], u2[0]);
+      st[5] = make_double2(u2[1], u2[2]);
+      st[6] = make_double2(inv, sqrt(2.0 * coe) * inv);           // [13] sqrt(coe*|w0|), w0 = -2/NN^2 (bavoxel.hpp:385)
+      st[7] = make_double2(sqrt(2.0 * coe / (lam[1] - lam[0])),   // [14] sqrt(coe*|w1|), w1 = 2/(l0-l1) (bavoxel.hpp:392)
+                           sqrt(2.0 * coe / (lam[2] - lam[0])));
+      st[8] = make_double2(coe, lam[0]);
+      st[9] = make_double2(lam[1], lam[2]);
+    }
+  }
+  res_acc = warp_sum(res_acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = res_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) res_part[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
 // deterministic sum of the per-CTA residual partials (single warp)
 __global__ void residual_reduce_kernel(const double *part, int nparts, double *out, int accumulate) {
   double s = 0.0;
@@ -394,6 +490,18 @@ int launch_voxel_stats(balm_ctx *c, const double *poses, int64_t v0, int64_t v1,
               stats_out, c->res_part};
   const int psmem = 12 * c->N * (int)sizeof(double);
   const bool in_smem = psmem <= 64 * 1024;  // up to 682 poses; larger windows read the table through L1
+  if (c->vsums) {  // default: streaming kernel + one eigen-solve per thread (BALM_NO_STATS_SPLIT: single kernel below)
+    if (in_smem) voxel_sums_kernel<true><<<blocks, STATS_THREADS, psmem, c->stream>>>(a, c->vsums);
+    else voxel_sums_kernel<false><<<blocks, STATS_THREADS, 0, c->stream>>>(a, c->vsums);
+    const int64_t wantb = (nv + 127) / 128;
+    const int eb = (int)(wantb < (int64_t)c->res_blocks ? wantb : c->res_blocks);
+    if (store_stats) voxel_eig_kernel<true><<<eb, 128, 0, c->stream>>>(c->vsums, c->coe, v0, v1, stats_out, c->res_part);
+    else voxel_eig_kernel<false><<<eb, 128, 0, c->stream>>>(c->vsums, c->coe, v0, v1, nullptr, c->res_part);
+    residual_reduce_kernel<<<1, 32, 0, c->stream>>>(c->res_part, eb, residual_out_dev, 1);
+    c->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return BALM_OK;
+  }
   if (in_smem) {
     if (store_stats) voxel_stats_kernel<true, true><<<blocks, STATS_THREADS, psmem, c->stream>>>(a);
     else voxel_stats_kernel<false, true><<<blocks, STATS_THREADS, psmem, c->stream>>>(a);
@@ -514,5 +622,6 @@ int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bo
 int factor_kernels_setup() {
   CUDA_TRY(cudaFuncSetAttribute(voxel_stats_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CUDA_TRY(cudaFuncSetAttribute(voxel_stats_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(voxel_sums_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   return BALM_OK;
 }

@@ -76,6 +76,7 @@ struct balm_ctx {
   // ---- evaluation workspaces ----
   int64_t VB = 0;                 // voxels per batch
   double *stats = nullptr;        // [VB][20]
+  double *vsums = nullptr;        // [VB][10] per-voxel cluster sums (stats pass: streaming kernel -> eigen kernel)
   double *stats_trial = nullptr;  // [M][20] stats of the LM trial poses (single-batch problems): an accepted step
                                   // hands them to the next evaluation instead of recomputing them
   double *G = nullptr;            // [3*VB][ldg] fp64 scaled factor matrix G' (MN-major: pose index contiguous)
