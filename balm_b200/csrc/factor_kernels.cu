@@ -1,11 +1,13 @@
 // factor_kernels.cu -- the O(K) streaming passes of the eigen-factor evaluation (HBM-bound kernels K1-K3).
 //
-//   voxel_stats_kernel : per voxel  C = sum_i T_i C_i T_i^T (+fix), v_bar, eig(A)  -> residual (+ stats table)
+//   voxel_sums_kernel + voxel_eig_kernel (default) / voxel_stats_kernel (single-kernel form):
+//                        per voxel  C = sum_i T_i C_i T_i^T (+fix), v_bar, eig(A)  -> residual (+ stats table)
 //                        = VOX_HESS::evaluate_only_residual (bavoxel.hpp:428-470) and phase 1 of
 //                          left_evaluate_acc2 (bavoxel.hpp:322-360)
 //   obs_pass_kernel    : per observation  g_k^i, a_i, gradient and diagonal-block terms
 //                        = left_evaluate_acc2 per-observation loop (bavoxel.hpp:365-402); writes the scaled
-//                          factor matrix G' (3 rows per voxel, 6N columns) consumed by the SYRK
+//                          factor matrix G' (3 rows per voxel, 6N columns) consumed by the SYRK: as fp64 (OBS_FP64)
+//                          or directly as int8 digit planes (OBS_INT8 / OBS_FUSED, tensor path)
 //   obs_reduce_kernel  : fixed-order reduction of the per-chunk gradient / diagonal-block partials
 //
 // Layouts: observations SoA obs[c][s] (c<10, s in CSR order), so a warp reading 32 consecutive slots of one

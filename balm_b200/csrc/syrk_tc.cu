@@ -10,7 +10,9 @@
 // (S = 4) and the dropped digit pairs s+t >= S (same order); integer accumulation is associative, so the
 // result does not depend on tile order, k-splits or the number of GPUs.
 //
-// Kernel anatomy (one CTA per SM, persistent over (tile, k-split) items, 320 threads):
+// Kernel anatomy of the 1-SM kernel (syrk_tc_kernel; one CTA per SM, persistent over (tile, k-split) items, 320
+// threads). The default is syrk_tc_2sm_kernel further down: the same pipeline with 2-CTA clusters and
+// tcgen05.mma.cta_group::2 (M = 256 across the pair, each CTA holding half of the shared B block).
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor.3d of the S int8 planes of the A (rows bi) and B (rows bj)
 //              128-column blocks, 128B-swizzled, into a 192 KB shared-memory ring of 3-6 stages (mbarrier full/empty)
 //   warp 1   : MMA issuer    -- one elected lane issues tcgen05.mma.cta_group::1.kind::i8, M=128 N=128 K=32,
