@@ -50,13 +50,47 @@ def rsme(poses_es, poses_gt):
     return np.sqrt(rot / len(Re)), np.sqrt(tran / len(Re))
 
 
+def down_sampling_voxel(xyz, voxel_size):
+    """down_sampling_voxel of include/tools.hpp:203-242: one point per occupied voxel = the mean of its points (voxel
+    index from the float32 quotient with the "-1 for negatives" rule, truncated). The reference keeps a running float32
+    mean in hash-map order; here the mean is taken in float64 and the voxels come out sorted -- display data only."""
+    xyz = np.asarray(xyz, dtype=np.float32).reshape(-1, 3)
+    if voxel_size < 0.001 or len(xyz) == 0:
+        return xyz.copy()
+    loc = xyz / np.float32(voxel_size)
+    loc = np.where(loc < 0, loc - np.float32(1.0), loc)
+    key = np.trunc(loc).astype(np.int64)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    inv = inv.reshape(-1)
+    out = np.zeros((len(cnt), 3))
+    np.add.at(out, inv, xyz.astype(np.float64))
+    return (out / cnt[:, None]).astype(np.float32)
+
+
+def data_show(poses12, scans, voxel_size=0.05):
+    """The clouds data_show publishes (benchmark_realworld.cpp:108-142), returned instead: every scan down-sampled at
+    5 cm, moved to the world frame of pose 0, concatenated (-> /map_show), and the trajectory (-> /map_path, the scan
+    index in the curvature field)."""
+    R, p = unpack_poses(poses12)
+    R0, p0 = R[0].copy(), p[0].copy()
+    p = (p - p0) @ R0
+    R = np.einsum("ji,njk->nik", R0, R)
+    clouds = []
+    for i, s in enumerate(scans):
+        q = down_sampling_voxel(s, voxel_size).astype(np.float64)
+        clouds.append((q @ R[i].T + p[i]).astype(np.float32))
+    cloud = np.concatenate(clouds) if clouds else np.zeros((0, 3), np.float32)
+    return cloud, p.astype(np.float32)
+
+
 def _print_trace(trace):
     for i, t in enumerate(trace):  # the line of bavoxel.hpp:1132 / benchmark_virtual.cpp:432
         rho = t["q"] / t["q1"] if t["q1"] != 0 else float("nan")
         print("iter%d: (%f %f) u: %f v: %.1f q: %.3f %f %f" % (i, t["r1"], t["r2"], t["u"], t["v"], rho, t["q1"], t["q"]))
 
 
-def benchmark_realworld(file_path, voxel_size=2.0, device=0, precision=L.PREC_TENSOR, max_scans=None, quiet=False):
+def benchmark_realworld(file_path, voxel_size=2.0, device=0, precision=L.PREC_TENSOR, max_scans=None, quiet=False,
+                        keep_scans=False):
     """file_path: the directory holding alidarPose.csv and full<i>.pcd (the reference appends
     "/datas/benchmark_realworld/" to its package path, benchmark_realworld.cpp:77).
     Returns dict(poses_init, poses, trace, n_voxels, n_obs, seconds) or None when the plane guard fires."""
@@ -104,8 +138,11 @@ def benchmark_realworld(file_path, voxel_size=2.0, device=0, precision=L.PREC_TE
     if not quiet:
         _print_trace(trace)
         print("\nread %.2f s, association %.3f s, optimisation %.3f s" % (t_read - t0, t_cut - t_read, t_ba - t_cut))
-    return dict(poses_init=poses_init, poses=poses, trace=trace, n_voxels=n_vox, n_obs=n_obs,
-                seconds=dict(read=t_read - t0, association=t_cut - t_read, optimisation=t_ba - t_cut))
+    res = dict(poses_init=poses_init, poses=poses, trace=trace, n_voxels=n_vox, n_obs=n_obs,
+               seconds=dict(read=t_read - t0, association=t_cut - t_read, optimisation=t_ba - t_cut))
+    if keep_scans:
+        res["scans"] = scans
+    return res
 
 
 def benchmark_virtual(winSize=20, sufSize=150, ptsSize=40, point_noise=0.05, surf_range=2.0, seed=10, device=0,

@@ -78,3 +78,34 @@ def test_reads_the_reference_dataset():
     assert len(R) == 177 and np.allclose(np.einsum("nij,nkj->nik", R, R), np.eye(3), atol=1e-5)  # the csv stores six decimals
     xyz = io.read_pcd(os.path.join(d, "full0.pcd"))
     assert xyz.dtype == np.float32 and xyz.shape[1] == 3 and len(xyz) > 10000 and np.isfinite(xyz).all()
+
+
+def test_down_sampling_voxel_matches_the_sequential_definition():
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(0, 0.2, (3000, 3)).astype(np.float32)
+    vs = 0.05
+    got = drivers.down_sampling_voxel(xyz, vs)
+    cells = {}
+    for q in xyz:  # tools.hpp:209-234, literally (float32 state)
+        loc = q / np.float32(vs)
+        loc = np.where(loc < 0, loc - np.float32(1.0), loc)
+        k = tuple(int(x) for x in np.trunc(loc))
+        if k not in cells:
+            cells[k] = [q.copy(), np.float32(1.0)]
+        else:
+            m, c = cells[k]
+            cells[k] = [(m * c + q) / (c + np.float32(1.0)), c + np.float32(1.0)]
+    want = np.array([cells[k][0] for k in sorted(cells)])
+    assert got.shape == want.shape and np.abs(got - want).max() < 2e-6
+    assert drivers.down_sampling_voxel(xyz, 0.0).shape == xyz.shape          # below 1 mm: untouched (:205)
+
+
+def test_data_show_reanchors_and_concatenates():
+    R = np.stack([scenes.exp_so3(np.array([0.0, 0.0, 0.3 * i])) for i in range(3)])
+    p = np.array([[1.0, 2.0, 3.0], [2.0, 2.0, 3.0], [3.0, 2.0, 3.0]])
+    scans = [np.array([[1.0, 0.0, 0.0]], dtype=np.float32)] * 3
+    cloud, path = drivers.data_show(drivers.pack_poses(R, p), scans)
+    assert cloud.shape == (3, 3) and path.shape == (3, 3)
+    assert np.allclose(path[0], 0) and np.allclose(path[2], [2, 0, 0], atol=1e-6)
+    assert np.allclose(cloud[0], [1, 0, 0], atol=1e-6)
+    assert np.allclose(cloud[1], R[1] @ [1, 0, 0] + [1, 0, 0], atol=1e-6)
