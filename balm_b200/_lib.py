@@ -47,7 +47,7 @@ SYMBOLS = ["balm_last_error", "balm_version", "balm_create", "balm_destroy", "ba
            "balm_set_voxels_dev", "balm_evaluate", "balm_residual", "balm_solve", "balm_damping_iter",
            "balm_default_lm_opts", "balm_comm_unique_id", "balm_comm_init", "balm_get_timings",
            "balm_reset_counters", "balm_sync", "balm_timer_begin", "balm_timer_end", "balm_device_views", "balm_synth_virtual",
-           "balm_download_voxels", "balm_num_obs", "balm_default_assoc_opts", "balm_cut_voxels"]
+           "balm_download_voxels", "balm_download_voxel_range", "balm_num_obs", "balm_default_assoc_opts", "balm_cut_voxels"]
 
 
 def lib():
@@ -82,6 +82,7 @@ def lib():
         L.balm_synth_virtual.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double,
                                          C.c_uint64, C.c_void_p, C.c_void_p]
         L.balm_download_voxels.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.balm_download_voxel_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 4 + [C.POINTER(C.c_int64)]
         L.balm_default_assoc_opts.argtypes = [C.POINTER(AssocOpts)]
         L.balm_cut_voxels.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AssocOpts),
                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

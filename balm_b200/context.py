@@ -70,6 +70,18 @@ class Context:
         L.check(L.lib().balm_download_voxels(self._h, _p(row_ptr), _p(pose_idx), _p(obs10), _p(coe)))
         return row_ptr, pose_idx, obs10, coe
 
+    def download_voxel_range(self, head, end):
+        """CSR arrays of voxels [head, end) only (row_ptr re-based to 0)."""
+        K = C.c_int64()
+        L.check(L.lib().balm_download_voxel_range(self._h, int(head), int(end), None, None, None, None, C.byref(K)))
+        row_ptr = np.zeros(end - head + 1, dtype=np.int64)
+        pose_idx = np.zeros(K.value, dtype=np.int32)
+        obs10 = np.zeros((K.value, 10))
+        coe = np.zeros(end - head)
+        L.check(L.lib().balm_download_voxel_range(self._h, int(head), int(end), _p(row_ptr), _p(pose_idx), _p(obs10),
+                                                  _p(coe), C.byref(K)))
+        return row_ptr, pose_idx, obs10, coe
+
     # ---- evaluation ----
     def evaluate(self, poses12, head=0, end=None, include_fix=False, want_H=True):
         poses12 = np.ascontiguousarray(poses12, dtype=np.float64)

@@ -154,10 +154,6 @@ struct LevelTables {  // device arrays of one layer
   int *node_start = nullptr;       // [nnode] first segment
   unsigned long long *node_key = nullptr;
   int *node_size = nullptr, *node_planar = nullptr, *node_nframes = nullptr, *node_leaf = nullptr;
-  void release() {
-    cudaFree(segB); cudaFree(seg_frame); cudaFree(node_start); cudaFree(node_key); cudaFree(node_size);
-    cudaFree(node_planar); cudaFree(node_nframes); cudaFree(node_leaf);
-  }
 };
 
 __device__ __forceinline__ int find_key(const unsigned long long *keys, int n, unsigned long long k) {
@@ -230,11 +226,24 @@ __global__ void emit_kernel(const int *ref, const int *obs_start, int nleaf, Emi
   }
 }
 
-template <typename T>
-int dalloc(T **p, size_t n) {
-  CUDA_TRY(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
-  return BALM_OK;
-}
+// Every scratch buffer of assoc_build lives in a pool that frees what is left on ANY exit path (the early returns of
+// ATRY / CUDA_TRY, "no plane voxels found", a bad frame index ...), so a failed call leaks nothing.
+struct ScratchPool {
+  std::vector<void *> ptrs;
+  ~ScratchPool() { for (void *q : ptrs) cudaFree(q); }
+  template <typename T>
+  int get(T **p, size_t n) {
+    CUDA_TRY(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
+    ptrs.push_back((void *)*p);
+    return BALM_OK;
+  }
+  void drop(void *q) {
+    if (!q) return;
+    for (size_t i = 0; i < ptrs.size(); i++)
+      if (ptrs[i] == q) { ptrs[i] = ptrs.back(); ptrs.pop_back(); break; }
+    cudaFree(q);
+  }
+};
 #define ATRY(x) do { int _s = (x); if (_s != BALM_OK) return _s; } while (0)
 
 }  // namespace
@@ -249,17 +258,18 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
     return BALM_ERR_INVALID;
   }
   cudaStream_t st = c->stream;
+  ScratchPool pool;
   AssocParams P{voxel_size, layer_limit, min_ps, {eig3[0], eig3[1], eig3[2]}};
   float *xyz = nullptr;
   int *frame = nullptr, *idx = nullptr, *idx2 = nullptr, *flag = nullptr, *scan = nullptr, *seg_start = nullptr, *bad = nullptr;
   unsigned *fkey = nullptr, *fkey2 = nullptr;
   unsigned long long *key = nullptr, *keyL = nullptr, *keyL2 = nullptr;
   double *poses = nullptr;
-  ATRY(dalloc(&xyz, (size_t)3 * n)); ATRY(dalloc(&frame, (size_t)n)); ATRY(dalloc(&idx, (size_t)n)); ATRY(dalloc(&idx2, (size_t)n));
-  ATRY(dalloc(&flag, (size_t)n)); ATRY(dalloc(&scan, (size_t)n)); ATRY(dalloc(&seg_start, (size_t)n)); ATRY(dalloc(&bad, 1));
-  ATRY(dalloc(&fkey, (size_t)n)); ATRY(dalloc(&fkey2, (size_t)n));
-  ATRY(dalloc(&key, (size_t)n)); ATRY(dalloc(&keyL, (size_t)n)); ATRY(dalloc(&keyL2, (size_t)n));
-  ATRY(dalloc(&poses, (size_t)12 * c->N));
+  ATRY(pool.get(&xyz, (size_t)3 * n)); ATRY(pool.get(&frame, (size_t)n)); ATRY(pool.get(&idx, (size_t)n)); ATRY(pool.get(&idx2, (size_t)n));
+  ATRY(pool.get(&flag, (size_t)n)); ATRY(pool.get(&scan, (size_t)n)); ATRY(pool.get(&seg_start, (size_t)n)); ATRY(pool.get(&bad, 1));
+  ATRY(pool.get(&fkey, (size_t)n)); ATRY(pool.get(&fkey2, (size_t)n));
+  ATRY(pool.get(&key, (size_t)n)); ATRY(pool.get(&keyL, (size_t)n)); ATRY(pool.get(&keyL2, (size_t)n));
+  ATRY(pool.get(&poses, (size_t)12 * c->N));
   CUDA_TRY(cudaMemcpyAsync(xyz, xyz_h, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(frame, frame_h, sizeof(int) * n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(poses, poses12_h, sizeof(double) * 12 * c->N, cudaMemcpyHostToDevice, st));
@@ -274,8 +284,8 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   cub::DeviceRadixSort::SortPairs(nullptr, tb2, keyL, keyL2, idx, idx2, (int)n, 0, 63, st);
   cub::DeviceScan::ExclusiveSum(nullptr, tb3, flag, scan, (int)n, st);
   tmp_bytes = std::max(tmp_bytes, std::max(tb2, tb3));
-  void *tmp = nullptr;
-  CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
+  char *tmp = nullptr;
+  ATRY(pool.get(&tmp, tmp_bytes));
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, fkey, fkey2, idx, idx2, (int)n, 0, 32, st));
   int *order = idx2;   // frame-sorted point order
   int *work = idx;     // per-level sorted order
@@ -298,27 +308,27 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
     double *segW = nullptr;
     unsigned long long *seg_key = nullptr;
     int *nflag = nullptr, *nscan = nullptr;
-    ATRY(dalloc(&t.segB, (size_t)10 * nseg)); ATRY(dalloc(&segW, (size_t)10 * nseg)); ATRY(dalloc(&t.seg_frame, (size_t)nseg));
-    ATRY(dalloc(&seg_key, (size_t)nseg)); ATRY(dalloc(&nflag, (size_t)nseg)); ATRY(dalloc(&nscan, (size_t)nseg));
+    ATRY(pool.get(&t.segB, (size_t)10 * nseg)); ATRY(pool.get(&segW, (size_t)10 * nseg)); ATRY(pool.get(&t.seg_frame, (size_t)nseg));
+    ATRY(pool.get(&seg_key, (size_t)nseg)); ATRY(pool.get(&nflag, (size_t)nseg)); ATRY(pool.get(&nscan, (size_t)nseg));
     const unsigned gs = (unsigned)((nseg + 127) / 128);
     seg_reduce_kernel<<<gs, 128, 0, st>>>(xyz, frame, poses, work, keyL2, seg_start, nseg, n, t.segB, segW, t.seg_frame, seg_key);
     node_flag_kernel<<<gs, 128, 0, st>>>(seg_key, nseg, nflag);
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, nflag, nscan, nseg, st);
-    if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+    if (tb > tmp_bytes) { pool.drop(tmp); tmp = nullptr; tmp_bytes = tb; ATRY(pool.get(&tmp, tmp_bytes)); }
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nflag, nscan, nseg, st));
     CUDA_TRY(cudaMemcpyAsync(&last_flag, nflag + nseg - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&last_scan, nscan + nseg - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     t.nnode = last_scan + last_flag;
-    ATRY(dalloc(&t.node_start, (size_t)t.nnode)); ATRY(dalloc(&t.node_key, (size_t)t.nnode));
-    ATRY(dalloc(&t.node_size, (size_t)t.nnode)); ATRY(dalloc(&t.node_planar, (size_t)t.nnode));
-    ATRY(dalloc(&t.node_nframes, (size_t)t.nnode)); ATRY(dalloc(&t.node_leaf, (size_t)t.nnode));
+    ATRY(pool.get(&t.node_start, (size_t)t.nnode)); ATRY(pool.get(&t.node_key, (size_t)t.nnode));
+    ATRY(pool.get(&t.node_size, (size_t)t.nnode)); ATRY(pool.get(&t.node_planar, (size_t)t.nnode));
+    ATRY(pool.get(&t.node_nframes, (size_t)t.nnode)); ATRY(pool.get(&t.node_leaf, (size_t)t.nnode));
     seg_start_kernel<<<gs, 128, 0, st>>>(nflag, nscan, nseg, t.node_start);
     node_judge_kernel<<<(unsigned)((t.nnode + 127) / 128), 128, 0, st>>>(segW, seg_key, t.node_start, t.nnode, nseg, P.eig[L],
                                                                         t.node_key, t.node_size, t.node_planar, t.node_nframes);
     CUDA_TRY(cudaStreamSynchronize(st));
-    cudaFree(segW); cudaFree(seg_key); cudaFree(nflag); cudaFree(nscan);
+    pool.drop(segW); pool.drop(seg_key); pool.drop(nflag); pool.drop(nscan);
     c->launches += 9;
   }
   int h_bad = 0;
@@ -337,10 +347,10 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
     leaf_decide_kernel<<<(unsigned)((t.nnode + 127) / 128), 128, 0, st>>>(
         L, t.nnode, t.node_key, t.node_size, t.node_planar, t.node_nframes, T[0].node_key, T[0].node_size, T[0].node_planar,
         T[0].nnode, T[1].node_key, T[1].node_size, T[1].node_planar, T[1].nnode, min_ps, layer_limit, t.node_leaf);
-    ATRY(dalloc(&lscan[L], (size_t)t.nnode));
+    ATRY(pool.get(&lscan[L], (size_t)t.nnode));
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, t.node_leaf, lscan[L], t.nnode, st);
-    if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+    if (tb > tmp_bytes) { pool.drop(tmp); tmp = nullptr; tmp_bytes = tb; ATRY(pool.get(&tmp, tmp_bytes)); }
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, t.node_leaf, lscan[L], t.nnode, st));
     int a = 0, b = 0;
     CUDA_TRY(cudaMemcpyAsync(&a, t.node_leaf + t.nnode - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -352,8 +362,8 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   if (nleaf < 1) { balm_set_error("balm_cut_voxels: no plane voxels found"); return BALM_ERR_INVALID; }
   unsigned long long *lkey = nullptr, *lkey2 = nullptr;
   int *lref = nullptr, *lref2 = nullptr, *lcnt = nullptr, *lobs = nullptr;
-  ATRY(dalloc(&lkey, (size_t)nleaf)); ATRY(dalloc(&lkey2, (size_t)nleaf)); ATRY(dalloc(&lref, (size_t)nleaf));
-  ATRY(dalloc(&lref2, (size_t)nleaf)); ATRY(dalloc(&lcnt, (size_t)nleaf)); ATRY(dalloc(&lobs, (size_t)nleaf));
+  ATRY(pool.get(&lkey, (size_t)nleaf)); ATRY(pool.get(&lkey2, (size_t)nleaf)); ATRY(pool.get(&lref, (size_t)nleaf));
+  ATRY(pool.get(&lref2, (size_t)nleaf)); ATRY(pool.get(&lcnt, (size_t)nleaf)); ATRY(pool.get(&lobs, (size_t)nleaf));
   int base = 0;
   for (int L = 0; L <= layer_limit; L++) {
     leaf_collect_kernel<<<(unsigned)((T[L].nnode + 127) / 128), 128, 0, st>>>(L, T[L].nnode, T[L].node_leaf, lscan[L],
@@ -363,7 +373,7 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   {
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, lkey, lkey2, lref, lref2, nleaf, 0, 63, st);
-    if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+    if (tb > tmp_bytes) { pool.drop(tmp); tmp = nullptr; tmp_bytes = tb; ATRY(pool.get(&tmp, tmp_bytes)); }
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lkey, lkey2, lref, lref2, nleaf, 0, 63, st));
   }
   leaf_count_kernel<<<(unsigned)((nleaf + 127) / 128), 128, 0, st>>>(lref2, nleaf, T[0].node_nframes, T[1].node_nframes,
@@ -371,7 +381,7 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   {
     size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, lcnt, lobs, nleaf, st);
-    if (tb > tmp_bytes) { cudaFree(tmp); tmp_bytes = tb; CUDA_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+    if (tb > tmp_bytes) { pool.drop(tmp); tmp = nullptr; tmp_bytes = tb; ATRY(pool.get(&tmp, tmp_bytes)); }
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, lcnt, lobs, nleaf, st));
   }
   int a = 0, b = 0;
@@ -387,10 +397,7 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   c->launches += 12;
-  for (int L = 0; L < 3; L++) { T[L].release(); cudaFree(lscan[L]); }
-  cudaFree(xyz); cudaFree(frame); cudaFree(idx); cudaFree(idx2); cudaFree(flag); cudaFree(scan); cudaFree(seg_start);
-  cudaFree(bad); cudaFree(fkey); cudaFree(fkey2); cudaFree(key); cudaFree(keyL); cudaFree(keyL2); cudaFree(poses);
-  cudaFree(tmp); cudaFree(lkey); cudaFree(lkey2); cudaFree(lref); cudaFree(lref2); cudaFree(lcnt); cudaFree(lobs);
+  // the pool's destructor frees every scratch buffer (level tables included)
   *M_out = nleaf;
   *K_out = K;
   return BALM_OK;

@@ -68,6 +68,7 @@ static void free_problem(balm_ctx *c) {
   c->stats = c->stats_trial = c->G = c->obs_part = c->syrk_part = nullptr;
   tensor_syrk_free(c);
   c->M = c->K = c->Kp = 0;
+  c->registered = false;
 }
 
 static int alloc_problem_arrays(balm_ctx *c, int64_t M, int64_t K, bool with_fix) {
@@ -194,6 +195,7 @@ extern "C" int balm_create(balm_ctx **out, int n_poses, int device, int precisio
   TRY(dev_alloc(&c->dvec, n));
   TRY(dev_alloc(&c->scal, 32));
   TRY(dev_alloc(&c->flags, 4));
+  TRY(dev_alloc(&c->planes, 2 * (size_t)c->N));
   TRY(dev_alloc(&c->accum, (size_t)BALM_ACC * c->Np));
   TRY(dev_alloc(&c->accum_batch, (size_t)BALM_ACC * c->Np));
   c->res_blocks = c->sm_count * 24;  // residual partials: one per warp of the stats kernel (3 CTAs x 8 warps per SM)
@@ -213,7 +215,7 @@ extern "C" int balm_destroy(balm_ctx *c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaFree(c->poses); cudaFree(c->poses_trial); cudaFree(c->H); cudaFree(c->A); cudaFree(c->W);
   cudaFree(c->dx); cudaFree(c->dvec); cudaFree(c->scal); cudaFree(c->flags); cudaFree(c->accum); cudaFree(c->accum_batch);
-  cudaFree(c->res_part); cudaFree(c->Xinv); cudaFree(c->dinv); cudaFree(c->sol); cudaFree(c->ysol);
+  cudaFree(c->res_part); cudaFree(c->planes); cudaFree(c->Xinv); cudaFree(c->dinv); cudaFree(c->sol); cudaFree(c->ysol);
   if (c->solve_graph) cudaGraphExecDestroy((cudaGraphExec_t)c->solve_graph);
   cudaFreeHost(c->h_scal); cudaFreeHost(c->h_flags);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -259,9 +261,8 @@ __global__ void pose_hist_kernel(const int *pose_idx, int64_t K, int N, int *pla
 static int finish_registration(balm_ctx *c) {
   const int N = c->N;
   const int64_t M = c->M;
-  int *d_out = nullptr, *d_planes = nullptr;
+  int *d_out = nullptr, *d_planes = c->planes;  // c->planes [N]: per-pose voxel counts, kept for the collective guard
   TRY(dev_alloc(&d_out, 4));
-  TRY(dev_alloc(&d_planes, (size_t)N));
   CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(int) * 4, c->stream));
   CUDA_TRY(cudaMemsetAsync(d_planes, 0, sizeof(int) * N, c->stream));
   csr_check_kernel<<<(unsigned)((M + 127) / 128), 128, 0, c->stream>>>(c->row_ptr, c->pose_idx, M, N, d_out);
@@ -272,7 +273,7 @@ static int finish_registration(balm_ctx *c) {
   CUDA_TRY(cudaMemcpyAsync(h_out, d_out, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaMemcpyAsync(planes.data(), d_planes, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  cudaFree(d_out); cudaFree(d_planes);
+  cudaFree(d_out);
   if (h_out[0]) {
     free_problem(c);  // leave the context without a problem rather than with a malformed one
     balm_set_error("balm_set_voxels: pose_idx must be ascending and in [0,N) inside each voxel");
@@ -282,6 +283,7 @@ static int finish_registration(balm_ctx *c) {
   c->dense = dense;
   c->max_k = h_out[2];
   c->min_planes = *std::min_element(planes.begin(), planes.end());
+  c->registered = true;
   if (!dense) {  // pose-major lists for the observation pass (sparse problems are small: built on the host)
     std::vector<int64_t> row_ptr(M + 1);
     std::vector<int32_t> pidx(c->K);
@@ -342,6 +344,15 @@ static int upload_aos(balm_ctx *c, const double *aos, bool aos_on_device, double
   return BALM_OK;
 }
 
+// An empty voxel set: evaluations give H = 0, g = 0, r = 0 (and still take part in the all-reduce).
+static int register_empty(balm_ctx *c) {
+  free_problem(c);
+  CUDA_TRY(cudaMemsetAsync(c->planes, 0, sizeof(int) * c->N, c->stream));
+  c->dense = true; c->max_k = 0; c->min_planes = 0; c->VB = 0;
+  c->registered = true;
+  return BALM_OK;
+}
+
 static double host_ms() {
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -352,11 +363,12 @@ extern "C" int balm_set_voxels(balm_ctx *c, int64_t M, const int64_t *row_ptr, c
                                const double *obs10, const double *fix10, const double *coe) {
   const bool trace = getenv("BALM_TRACE_REG") != nullptr;  // host-side stage times of the registration
   const double t_begin = host_ms();
-  if (!c || M < 1 || !row_ptr || !pose_idx || !obs10 || !coe) {
+  if (!c || M < 0 || !row_ptr || (M > 0 && (!pose_idx || !obs10 || !coe))) {
     balm_set_error("balm_set_voxels: bad arguments");
     return BALM_ERR_INVALID;
   }
   CUDA_TRY(cudaSetDevice(c->device));
+  if (M == 0) return register_empty(c);  // a rank of a multi-GPU job whose shard holds no voxels still joins every collective
   const int64_t K = row_ptr[M];
   if (row_ptr[0] != 0 || K < M) { balm_set_error("balm_set_voxels: bad row_ptr"); return BALM_ERR_INVALID; }
   if (K >= ((int64_t)1 << 31)) { balm_set_error("balm_set_voxels: more than 2^31 observations per GPU"); return BALM_ERR_UNSUPPORTED; }
@@ -387,6 +399,13 @@ extern "C" int balm_set_voxels_dev(balm_ctx *c, int64_t M, const int64_t *row_pt
     return BALM_ERR_INVALID;
   }
   CUDA_TRY(cudaSetDevice(c->device));
+  {  // the same checks the host path makes on row_ptr / K (the per-voxel invariants are checked by csr_check_kernel)
+    int64_t ends[2] = {-1, -1};
+    CUDA_TRY(cudaMemcpy(&ends[0], row_ptr_dev, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&ends[1], row_ptr_dev + M, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (ends[0] != 0 || ends[1] != K) { balm_set_error("balm_set_voxels_dev: row_ptr[0] != 0 or row_ptr[M] != n_obs"); return BALM_ERR_INVALID; }
+    if (K >= ((int64_t)1 << 31)) { balm_set_error("balm_set_voxels_dev: more than 2^31 observations per GPU"); return BALM_ERR_UNSUPPORTED; }
+  }
   TRY(alloc_problem_arrays(c, M, K, fix10_dev != nullptr));
   CUDA_TRY(cudaMemcpyAsync(c->row_ptr, row_ptr_dev, sizeof(int64_t) * (M + 1), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->pose_idx, pose_idx_dev, sizeof(int32_t) * K, cudaMemcpyDeviceToDevice, c->stream));
@@ -417,6 +436,9 @@ extern "C" int balm_cut_voxels(balm_ctx *c, int64_t n_points, const float *xyz, 
   CUDA_TRY(cudaSetDevice(c->device));
   balm_assoc_opts o;
   if (opts) o = *opts; else balm_default_assoc_opts(&o);
+  // the reference keeps the planarity thresholds in a `float eigen_value_array[]` (bavoxel.hpp:11) and compares the
+  // double ratio with the promoted float (bavoxel.hpp:697): 1/9 is (double)(float)(1.0/9), not the double 1/9
+  for (double &e : o.eigen_value_array) e = (double)(float)e;
   int64_t M = 0, K = 0;
   TRY(assoc_build(c, n_points, xyz, frame, poses12, o.voxel_size, o.layer_limit, o.min_ps, o.eigen_value_array, &M, &K,
                   assoc_register));
@@ -425,25 +447,41 @@ extern "C" int balm_cut_voxels(balm_ctx *c, int64_t n_points, const float *xyz, 
   return finish_registration(c);
 }
 
-extern "C" int balm_download_voxels(balm_ctx *c, int64_t *row_ptr, int32_t *pose_idx, double *obs10, double *coe) {
+extern "C" int balm_download_voxel_range(balm_ctx *c, int64_t head, int64_t end, int64_t *row_ptr, int32_t *pose_idx,
+                                         double *obs10, double *coe, int64_t *n_obs_out) {
   if (!c || !c->obs) { balm_set_error("balm_download_voxels: no voxels registered"); return BALM_ERR_INVALID; }
+  if (head < 0 || end > c->M || head > end) { balm_set_error("balm_download_voxel_range: bad voxel range"); return BALM_ERR_INVALID; }
   CUDA_TRY(cudaSetDevice(c->device));
-  if (row_ptr) CUDA_TRY(cudaMemcpy(row_ptr, c->row_ptr, sizeof(int64_t) * (c->M + 1), cudaMemcpyDeviceToHost));
-  if (pose_idx) CUDA_TRY(cudaMemcpy(pose_idx, c->pose_idx, sizeof(int32_t) * c->K, cudaMemcpyDeviceToHost));
-  if (coe) CUDA_TRY(cudaMemcpy(coe, c->coe, sizeof(double) * c->M, cudaMemcpyDeviceToHost));
-  if (obs10) {
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  int64_t s0 = 0, s1 = 0;
+  CUDA_TRY(cudaMemcpy(&s0, c->row_ptr + head, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&s1, c->row_ptr + end, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  const int64_t K = s1 - s0;
+  if (n_obs_out) *n_obs_out = K;
+  if (row_ptr) {  // re-based to 0, like a freshly registered problem of end-head voxels
+    CUDA_TRY(cudaMemcpy(row_ptr, c->row_ptr + head, sizeof(int64_t) * (end - head + 1), cudaMemcpyDeviceToHost));
+    for (int64_t v = 0; v <= end - head; v++) row_ptr[v] -= s0;
+  }
+  if (pose_idx && K) CUDA_TRY(cudaMemcpy(pose_idx, c->pose_idx + s0, sizeof(int32_t) * K, cudaMemcpyDeviceToHost));
+  if (coe && end > head) CUDA_TRY(cudaMemcpy(coe, c->coe + head, sizeof(double) * (end - head), cudaMemcpyDeviceToHost));
+  if (obs10 && K) {
     const int64_t chunk = 1 << 22;
     double *scratch = nullptr;
-    TRY(dev_alloc(&scratch, (size_t)std::min(chunk, c->K) * 10));
-    for (int64_t b = 0; b < c->K; b += chunk) {
-      const int64_t m = std::min(chunk, c->K - b);
-      soa_to_aos_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(c->obs + b, scratch, m, c->Kp);
+    TRY(dev_alloc(&scratch, (size_t)std::min(chunk, K) * 10));
+    for (int64_t b = 0; b < K; b += chunk) {
+      const int64_t m = std::min(chunk, K - b);
+      soa_to_aos_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(c->obs + s0 + b, scratch, m, c->Kp);
       CUDA_TRY(cudaMemcpyAsync(obs10 + b * 10, scratch, sizeof(double) * m * 10, cudaMemcpyDeviceToHost, c->stream));
       CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
     cudaFree(scratch);
   }
   return BALM_OK;
+}
+
+extern "C" int balm_download_voxels(balm_ctx *c, int64_t *row_ptr, int32_t *pose_idx, double *obs10, double *coe) {
+  if (!c || !c->obs) { balm_set_error("balm_download_voxels: no voxels registered"); return BALM_ERR_INVALID; }
+  return balm_download_voxel_range(c, 0, c->M, row_ptr, pose_idx, obs10, coe, nullptr);
 }
 
 extern "C" int balm_synth_virtual(balm_ctx *c, int64_t M, int64_t first_voxel, int pts, double noise, double range,
@@ -463,6 +501,11 @@ extern "C" int balm_synth_virtual(balm_ctx *c, int64_t M, int64_t first_voxel, i
   c->dense = true;
   c->max_k = c->N;
   c->min_planes = (int)std::min<int64_t>(M, 1 << 30);
+  {
+    std::vector<int> pl((size_t)c->N, c->min_planes);
+    CUDA_TRY(cudaMemcpy(c->planes, pl.data(), sizeof(int) * c->N, cudaMemcpyHostToDevice));
+  }
+  c->registered = true;
   return alloc_workspaces(c);
 }
 
@@ -482,7 +525,7 @@ static int allreduce_sum(balm_ctx *c, double *buf, size_t count) {
 // pass of an accepted LM step, or by the evaluation before a rejected one) and c->scal[BALM_SCAL_RCUR] this rank's residual.
 static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t end, bool include_fix,
                         bool stats_cached = false) {
-  if (!c->obs) { balm_set_error("no voxels registered"); return BALM_ERR_INVALID; }
+  if (!c->registered) { balm_set_error("no voxels registered"); return BALM_ERR_INVALID; }
   if (head < 0 || end > c->M || head > end) { balm_set_error("evaluate: bad voxel range"); return BALM_ERR_INVALID; }
   double *r_dev = c->g + c->n;  // contiguous with H and g -> one all-reduce
   CUDA_TRY(cudaMemsetAsync(r_dev, 0, sizeof(double), c->stream));
@@ -492,10 +535,10 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
   // the tensor path's flags after the iteration's single synchronisation
   const bool deferred = c->defer && head == 0 && end == c->M && c->VB >= c->M && end > head;
   c->pending_stats_cached = stats_cached;
-  if (head == end) {  // empty range: H = 0
+  if (head == end) {  // empty range (or an empty shard): this rank contributes H = 0, g = 0, r = 0 -- and still enters
+    // the all-reduce below, which the other ranks of a multi-GPU job are waiting in
     CUDA_TRY(cudaMemsetAsync(c->H, 0, sizeof(double) * ((size_t)c->n * c->n + c->n + 1), c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->scal, 0, sizeof(double), c->stream));
-    return BALM_OK;
+    for (int e = 0; e <= 5; e++) CUDA_TRY(cudaEventRecord(c->ev[e], c->stream));
   }
   for (int64_t v0 = head; v0 < end; v0 += c->VB) {
     const int64_t v1 = std::min(end, v0 + c->VB);
@@ -524,9 +567,11 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
     first = false;
   }
   CUDA_TRY(cudaMemcpyAsync(c->scal + BALM_SCAL_RCUR, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));  // local, pre all-reduce
-  CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-  TRY(launch_assemble(c));
-  CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+  if (end > head) {
+    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+    TRY(launch_assemble(c));
+    CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
+  }
   TRY(allreduce_sum(c, c->H, (size_t)c->n * c->n + c->n + 1));
   CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->scal, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -558,7 +603,7 @@ static int collect_eval(balm_ctx *c) {
 }
 
 static int residual_dev(balm_ctx *c, const double *poses, double *host_out, bool keep_stats = false) {
-  if (!c->obs) { balm_set_error("no voxels registered"); return BALM_ERR_INVALID; }
+  if (!c->registered) { balm_set_error("no voxels registered"); return BALM_ERR_INVALID; }
   double *r_dev = c->scal + 2;
   CUDA_TRY(cudaEventRecord(c->ev[7], c->stream));
   CUDA_TRY(cudaMemsetAsync(r_dev, 0, sizeof(double), c->stream));
@@ -641,13 +686,22 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
   if (!c || !poses12 || !o) { balm_set_error("balm_damping_iter: bad arguments"); return BALM_ERR_INVALID; }
   CUDA_TRY(cudaSetDevice(c->device));
   if (n_iters) *n_iters = 0;
+  if (!c->registered) { balm_set_error("no voxels registered"); return BALM_ERR_INVALID; }
   if (o->min_planes_per_pose > 0) {  // bavoxel.hpp:1071-1085 (the shim reproduces the printf + exit(0))
-    long long local_min = c->min_planes;
-    if (c->world > 1) {  // a pose may be seen from other ranks' shards: the guard is on the global count,
-      // which the caller checks; per-rank we only refuse when even the sum of shards cannot reach it.
-      local_min = (long long)c->min_planes * c->world;
+    // The guard is on the GLOBAL count of voxels seeing each pose. With several ranks every rank all-reduces the
+    // per-pose histogram of its shard first, so all ranks take the same branch (a rank returning alone would leave
+    // the others waiting in the next collective).
+    long long global_min = c->min_planes;
+    if (c->world > 1 && c->comm) {
+      int *red = c->planes + c->N;
+      const int rc = g_nccl.AllReduce(c->planes, red, (size_t)c->N, /*ncclInt32*/ 2, /*ncclSum*/ 0, c->comm, c->stream);
+      if (rc != 0) { balm_set_error("ncclAllReduce (plane histogram) failed"); return BALM_ERR_NCCL; }
+      std::vector<int> pl((size_t)c->N);
+      CUDA_TRY(cudaMemcpyAsync(pl.data(), red, sizeof(int) * c->N, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      global_min = *std::min_element(pl.begin(), pl.end());
     }
-    if (local_min < o->min_planes_per_pose) {
+    if (global_min < o->min_planes_per_pose) {
       balm_set_error("Initial error too large. Please loose plane determination criteria for more planes.");
       return BALM_ERR_TOO_FEW_PLANES;
     }

@@ -54,6 +54,8 @@ struct balm_ctx {
   int *csc_ptr = nullptr, *csc_obs = nullptr, *csc_vox = nullptr;  // pose-major lists (sparse problems)
   int csc_max_len = 0;
   int min_planes = 0;             // min over poses of #voxels observing it (precheck, bavoxel.hpp:1071-1085)
+  int *planes = nullptr;          // [2][N] device: this rank's per-pose voxel counts | their all-reduced sum
+  bool registered = false;        // a voxel set (possibly empty: a rank whose shard has no voxels) is registered
 
   // ---- optimiser state (device) ----
   double *poses = nullptr, *poses_trial = nullptr;  // [12N]

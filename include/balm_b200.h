@@ -93,6 +93,8 @@ int balm_destroy(balm_ctx *ctx);
  * OCTO_TREE_NODE::tras_opt (bavoxel.hpp:908-929). Host arrays are copied (H2D) and may be freed on return. */
 int balm_set_voxels(balm_ctx *ctx, int64_t n_voxels, const int64_t *row_ptr, const int32_t *pose_idx,
                     const double *obs10, const double *fix10, const double *coe);
+/* n_voxels == 0 registers an EMPTY shard (row_ptr = {0}): evaluations contribute zeros and the rank still takes part
+ * in every collective of a multi-GPU job. */
 /* Same, but the arrays already live in device memory of ctx's GPU (used for HBM-resident timing). */
 int balm_set_voxels_dev(balm_ctx *ctx, int64_t n_voxels, const int64_t *row_ptr_dev, const int32_t *pose_idx_dev,
                         const double *obs10_dev, const double *fix10_dev, const double *coe_dev, int64_t n_obs);
@@ -157,6 +159,12 @@ int balm_synth_virtual(balm_ctx *ctx, int64_t n_voxels, int64_t first_voxel, int
 /* Copies the registered voxels back to host arrays (K*10, K, M+1, M) -- lets tests/bench feed the oracle and
  * the host-buffer (e2e) path with the very scene generated above. Any pointer may be NULL. */
 int balm_download_voxels(balm_ctx *ctx, int64_t *row_ptr, int32_t *pose_idx, double *obs10, double *coe);
+/* Same for the voxels [head, end) only (row_ptr re-based to 0: end-head+1 entries); n_obs_out receives the number of
+ * observations in the range, so a first call with NULL arrays sizes the buffers. Lets a parity test compare
+ * balm_evaluate(head, end) of a full-size problem (BASELINE C3: 4 GB of observations) with the CPU oracle on exactly
+ * the same voxels. */
+int balm_download_voxel_range(balm_ctx *ctx, int64_t head, int64_t end, int64_t *row_ptr, int32_t *pose_idx,
+                              double *obs10, double *coe, int64_t *n_obs_out);
 int64_t balm_num_obs(balm_ctx *ctx);
 
 #ifdef __cplusplus

@@ -52,7 +52,7 @@ def cut_voxels(points_body, frames, poses, **kw):
         c = pw_.sum(0) / n
         cov = pw_.T @ pw_ / n - np.outer(c, c)
         lam = np.linalg.eigvalsh(cov)
-        if lam[0] / lam[1] < o["eigen_value_array"][layer]:
+        if lam[0] / lam[1] < float(np.float32(o["eigen_value_array"][layer])):  # `float eigen_value_array[]`, bavoxel.hpp:11
             leaves.append((node_key(root, path[0], path[1]), pb_, fr_))
             return
         if layer == lim:

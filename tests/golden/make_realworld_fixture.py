@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 DATA = "/root/reference/datas/benchmark_realworld"
 N_POSES = int(os.environ.get("N_POSES", "48"))
 DECIMATE = int(os.environ.get("DECIMATE", "2"))
+OUT = os.environ.get("OUT", "realworld_voxels.npz")  # N_POSES=177 DECIMATE=12 OUT=realworld_c5_177.npz: every scan of the dataset
 VOXEL_SIZE = 2.0
 LAYER_LIMIT = 2
 MIN_PS = 15
@@ -74,7 +75,7 @@ def judge_eigen(node):
     c = p.sum(0) / n
     cov = p.T @ p / n - np.outer(c, c)
     lam = np.linalg.eigvalsh(cov)
-    return lam[0] / lam[1] < EIGEN_VALUE_ARRAY[node.layer]
+    return lam[0] / lam[1] < float(np.float32(EIGEN_VALUE_ARRAY[node.layer]))  # `float eigen_value_array[]` (bavoxel.hpp:11)
 
 
 def recut(node, out):
@@ -157,13 +158,17 @@ def main():
     assert st == 0
     H, g, r = o.evaluate_threads(poses12, threads=4)
     print("oracle LM:", [(round(t["r1"], 4), round(t["r2"], 4), t["accepted"]) for t in tr])
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "realworld_voxels.npz"),
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", OUT),
                         n_poses=N_POSES, row_ptr=row_ptr, pose_idx=pose_idx, obs10=obs10, coe=coe, poses_init=poses12,
                         oracle_poses=poses_out, oracle_r1=np.array([t["r1"] for t in tr]),
                         oracle_r2=np.array([t["r2"] for t in tr]),
                         oracle_accepted=np.array([t["accepted"] for t in tr]), oracle_residual0=r,
-                        oracle_g0=g, oracle_Hdiag0=np.diag(H).copy(), oracle_per_iter=per)
-    print("wrote", os.path.getsize(os.path.join(ROOT, "tests", "golden", "realworld_voxels.npz")), "bytes")
+                        oracle_g0=g, oracle_Hdiag0=np.diag(H).copy(), oracle_per_iter=per,
+                        # the whole Hessian is pinned through three probes (the GPU test also compares every entry with
+                        # the oracle run on the box): H 1, H w (w = fixed pseudo-random weights), Frobenius norm
+                        oracle_H0_rowsum=H @ np.ones(len(g)), oracle_H0_probe=H @ np.cos(np.arange(len(g)) * 0.7),
+                        oracle_H0_fro=np.linalg.norm(H))
+    print("wrote", os.path.getsize(os.path.join(ROOT, "tests", "golden", OUT)), "bytes")
 
 
 if __name__ == "__main__":

@@ -10,12 +10,16 @@ import pytest
 import scenes
 from oracle import oracle_py as orc
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "realworld_voxels.npz")
+GOLD_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# realworld_voxels.npz : first 48 scans, points decimated x2   (1002 voxels, 30 793 observations)
+# realworld_c5_177.npz : BASELINE config C5 at its real window: ALL 177 scans of datas/benchmark_realworld, points
+#                        decimated x12 (1606 voxels, 76 564 observations, co-visibility 2..177 poses per voxel)
+FIXTURES = ["realworld_voxels.npz", "realworld_c5_177.npz"]
 
 
-@pytest.fixture(scope="module")
-def gold():
-    d = np.load(GOLD)
+@pytest.fixture(scope="module", params=FIXTURES)
+def gold(request):
+    d = np.load(os.path.join(GOLD_DIR, request.param))
     return {k: d[k] for k in d.files}
 
 
@@ -25,6 +29,15 @@ def _pose_err(a, b):
     return rot, tra
 
 
+def _check_H_probes(H, gold, tol):
+    """Every entry of H enters the three committed probes (H 1, H w, ||H||_F)."""
+    n = H.shape[0]
+    scale = np.abs(H).max() * n
+    assert np.abs(H @ np.ones(n) - gold["oracle_H0_rowsum"]).max() <= tol * scale
+    assert np.abs(H @ np.cos(np.arange(n) * 0.7) - gold["oracle_H0_probe"]).max() <= tol * scale
+    assert abs(np.linalg.norm(H) - gold["oracle_H0_fro"]) <= tol * gold["oracle_H0_fro"]
+
+
 def test_oracle_reproduces_golden_vectors(gold):
     N = int(gold["n_poses"])
     o = orc.Oracle(N, gold["row_ptr"], gold["pose_idx"], gold["obs10"], gold["coe"])
@@ -32,6 +45,7 @@ def test_oracle_reproduces_golden_vectors(gold):
     assert abs(r - gold["oracle_residual0"]) <= 1e-12 * abs(r)
     assert np.abs(g - gold["oracle_g0"]).max() <= 1e-11 * np.abs(g).max()
     assert np.abs(np.diag(H) - gold["oracle_Hdiag0"]).max() <= 1e-11 * np.abs(np.diag(H)).max()
+    _check_H_probes(H, gold, 1e-11)
     st, poses, tr, per = o.damping_iter(gold["poses_init"], gauge_mode=0)
     assert st == 0 and [t["accepted"] for t in tr] == list(gold["oracle_accepted"].astype(bool))
     assert np.allclose([t["r2"] for t in tr], gold["oracle_r2"], rtol=1e-10)
@@ -52,7 +66,13 @@ def test_gpu_matches_golden_realworld(gold, prec):
     H, g, r = c.evaluate(gold["poses_init"])
     assert abs(r - gold["oracle_residual0"]) <= 1e-11 * abs(r)
     assert np.abs(g - gold["oracle_g0"]).max() <= 1e-10 * np.abs(g).max()
-    assert np.abs(np.diag(H) - gold["oracle_Hdiag0"]).max() <= (1e-9 if prec == 0 else 1e-8) * np.abs(np.diag(H)).max()
+    tolH = 1e-9 if prec == 0 else 1e-8
+    assert np.abs(np.diag(H) - gold["oracle_Hdiag0"]).max() <= tolH * np.abs(np.diag(H)).max()
+    # the WHOLE Hessian: against the committed probes and, entry by entry, against the oracle run on this box
+    _check_H_probes(H, gold, tolH)
+    Ho, go, ro = orc.Oracle(N, gold["row_ptr"], gold["pose_idx"], gold["obs10"], gold["coe"]).evaluate_threads(
+        gold["poses_init"], threads=4)
+    assert np.abs(H - Ho).max() <= tolH * np.abs(Ho).max() and np.array_equal(H, H.T)
     poses, tr, per = c.damping_iter(gold["poses_init"], gauge_mode=2, want_per_iter=True)
     assert [t["accepted"] for t in tr] == list(gold["oracle_accepted"].astype(bool))
     for it in range(len(tr)):

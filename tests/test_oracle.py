@@ -182,3 +182,28 @@ def test_damping_iter_precheck_too_few_planes():
     sc = scenes.make_scene(n_poses=4, n_planes=10, seed=12)
     st, _, _, _ = _oracle(sc).damping_iter(sc["poses_init"])
     assert st == 4  # reference prints and exit(0)s (bavoxel.hpp:1079-1085)
+
+
+@pytest.mark.parametrize("drop,with_fix", [(0.0, False), (0.4, False), (0.3, True)])
+def test_right_update_acc_evaluate2_pins_residual_and_gradient(drop, with_fix):
+    """Second reference-side pin: the right-update evaluator acc_evaluate2 (bavoxel.hpp:53-158,
+    restated in tests/numpy_acc2.py) gives the same residual as the left-update path and a gradient tied to the left
+    one by the per-pose adjoint map of bavoxel.hpp:279-300. Its own gradient is checked by finite differences of the
+    cost under the RIGHT update first, so the comparison is between two independently verified derivations."""
+    import numpy_acc2 as a2
+    sc = scenes.make_scene(n_poses=7, n_planes=30, seed=5, drop=drop, with_fix=with_fix, pts_size=12)
+    o = _oracle(sc)
+    x = sc["poses_init"]
+    gR, rR = a2.acc_evaluate2(sc["n_poses"], sc["row_ptr"], sc["pose_idx"], sc["obs10"], sc["coe"], x, sc["fix10"])
+    assert abs(rR - o.residual(x)) <= 1e-12 * abs(rR)          # evaluate_only_residual includes the fix cluster too
+    rng = np.random.default_rng(1)
+    for _ in range(4):                                           # central differences under R <- R Exp(phi), p <- p + dt
+        d = rng.normal(size=6 * sc["n_poses"])
+        d /= np.linalg.norm(d)
+        h = 1e-5
+        fd = (o.residual(a2.right_update(x, h * d, scenes.exp_so3)) -
+              o.residual(a2.right_update(x, -h * d, scenes.exp_so3))) / (2 * h)
+        assert abs(fd - gR @ d) <= 1e-6 * np.abs(gR).max()
+    Hl, gl, rl = o.evaluate(x, include_fix=True)                 # left gradient with the same treatment of the fix cluster
+    assert abs(rl - rR) <= 1e-12 * abs(rR)
+    assert np.abs(a2.left_to_right_gradient(gl, x) - gR).max() <= 1e-10 * np.abs(gR).max()

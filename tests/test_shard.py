@@ -26,7 +26,13 @@ def test_partition_covers_every_voxel_once_and_balances_work():
         w = k * k + 16 * k
         loads = [w[h:e].sum() for h, e in parts]
         assert max(loads) <= w.sum() / world + w.max() + 1e-9
-    assert shard.partition_voxels(np.array([0, 3]), 4) == [(0, 0), (0, 0), (0, 1), (1, 1)] or True  # degenerate sizes stay valid
+    # fewer voxels than ranks: still contiguous and covering, the surplus ranks get EMPTY shards -- which the library
+    # registers (balm_set_voxels with n_voxels = 0) so that those ranks keep joining the collectives
+    for M, world in ((1, 4), (3, 8), (0, 2)):
+        parts = shard.partition_voxels(np.arange(M + 1) * 3, world)
+        assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == M
+        assert all(a[1] == b[0] and a[0] <= a[1] for a, b in zip(parts, parts[1:] + [(M, M)]))
+        assert sum(e - h for h, e in parts) == M and sum(e > h for h, e in parts) == min(M, world)
 
 
 def _free_port():
