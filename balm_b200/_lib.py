@@ -26,7 +26,7 @@ class Timings(C.Structure):
                                          "ms_allreduce", "ms_solve", "ms_residual", "ms_update")] + \
                [("launches", C.c_int), ("n_eval", C.c_int), ("n_solve", C.c_int), ("n_residual", C.c_int),
                 ("digit_planes", C.c_int), ("single_sweeps", C.c_int), ("redone_sweeps", C.c_int),
-                ("n_stats", C.c_int)]
+                ("refinements", C.c_int), ("n_stats", C.c_int)]
 
 
 class AssocOpts(C.Structure):
@@ -46,7 +46,7 @@ _lib = None
 SYMBOLS = ["balm_last_error", "balm_version", "balm_create", "balm_destroy", "balm_set_voxels",
            "balm_set_voxels_dev", "balm_evaluate", "balm_residual", "balm_solve", "balm_damping_iter",
            "balm_default_lm_opts", "balm_comm_unique_id", "balm_comm_init", "balm_get_timings",
-           "balm_reset_counters", "balm_sync", "balm_timer_begin", "balm_timer_end", "balm_device_views", "balm_synth_virtual",
+           "balm_reset_counters", "balm_sync", "balm_timer_begin", "balm_timer_end", "balm_device_views", "balm_debug_dag_trace", "balm_synth_virtual",
            "balm_download_voxels", "balm_download_voxel_range", "balm_num_obs", "balm_default_assoc_opts", "balm_cut_voxels"]
 
 

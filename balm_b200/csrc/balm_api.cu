@@ -194,14 +194,15 @@ extern "C" int balm_create(balm_ctx **out, int n_poses, int device, int precisio
   TRY(dev_alloc(&c->dx, n));
   TRY(dev_alloc(&c->dvec, n));
   TRY(dev_alloc(&c->scal, 32));
-  TRY(dev_alloc(&c->flags, 4));
+  TRY(dev_alloc(&c->flags, 8));
   TRY(dev_alloc(&c->planes, 2 * (size_t)c->N));
   TRY(dev_alloc(&c->accum, (size_t)BALM_ACC * c->Np));
   TRY(dev_alloc(&c->accum_batch, (size_t)BALM_ACC * c->Np));
   c->res_blocks = c->sm_count * 24;  // residual partials: one per warp of the stats kernel (3 CTAs x 8 warps per SM)
   TRY(dev_alloc(&c->res_part, (size_t)c->res_blocks));
   CUDA_TRY(cudaMallocHost((void **)&c->h_scal, 16 * sizeof(double)));
-  CUDA_TRY(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int)));
+  CUDA_TRY(cudaMallocHost((void **)&c->h_flags, 8 * sizeof(int)));
+  memset(c->h_flags, 0, 8 * sizeof(int));
   for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
   *out = c;
   return BALM_OK;
@@ -216,6 +217,7 @@ extern "C" int balm_destroy(balm_ctx *c) {
   cudaFree(c->poses); cudaFree(c->poses_trial); cudaFree(c->H); cudaFree(c->A); cudaFree(c->W);
   cudaFree(c->dx); cudaFree(c->dvec); cudaFree(c->scal); cudaFree(c->flags); cudaFree(c->accum); cudaFree(c->accum_batch);
   cudaFree(c->res_part); cudaFree(c->planes); cudaFree(c->Xinv); cudaFree(c->dinv); cudaFree(c->sol); cudaFree(c->ysol);
+  cudaFree(c->Hpack); cudaFree(c->dval); cudaFree(c->rres); cudaFree(c->rdelta); cudaFree(c->dag_flags);
   if (c->solve_graph) cudaGraphExecDestroy((cudaGraphExec_t)c->solve_graph);
   cudaFreeHost(c->h_scal); cudaFreeHost(c->h_flags);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -510,6 +512,36 @@ extern "C" int balm_synth_virtual(balm_ctx *c, int64_t M, int64_t first_voxel, i
 }
 
 // ---------------- evaluation ----------------
+// Multi-GPU reduction of [H | g | r]: H is symmetric, so only its lower triangle travels. pack: column c of the lower
+// triangle (n - c entries, contiguous in H) -> offset c*n - c(c-1)/2 of the send buffer, followed by g and r;
+// unpack: the reduced triangle back into H, mirrored, plus g and r. 36 MB instead of 72 MB at N = 500.
+__global__ void pack_lower_kernel(const double *H, double *pack, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  const size_t tri = (size_t)n * (n + 1) / 2;
+  if (r < n && r >= c) pack[(size_t)c * n - (size_t)c * (c - 1) / 2 + (r - c)] = H[(size_t)c * n + r];
+  if (c == 0 && r <= n) pack[tri + r] = H[(size_t)n * n + r];  // g (n entries) and r (1 entry) follow H in the ctx buffer
+}
+__global__ void unpack_lower_kernel(const double *pack, double *H, int n) {
+  __shared__ double tile[32][33];
+  const int bc = blockIdx.y, br = blockIdx.x;  // 32 x 32 block (block row br >= block column bc)
+  if (br < bc) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int r = br * 32 + tx, c = bc * 32 + ty;
+  const size_t tri = (size_t)n * (n + 1) / 2;
+  double v = 0.0;
+  if (r < n && c < n && r >= c) {
+    v = pack[(size_t)c * n - (size_t)c * (c - 1) / 2 + (r - c)];
+    H[(size_t)c * n + r] = v;                      // lower element, coalesced in r
+  }
+  tile[ty][tx] = v;
+  __syncthreads();
+  const int r2 = br * 32 + ty, c2 = bc * 32 + tx;  // transposed read: upper element (row c2, col r2), coalesced in c2
+  if (r2 < n && c2 < n && r2 > c2) H[(size_t)r2 * n + c2] = tile[tx][ty];
+  if (br == 0 && bc == 0) {
+    for (int e = ty * 32 + tx; e <= n; e += 1024) H[(size_t)n * n + e] = pack[tri + e];
+  }
+}
+
 static int allreduce_sum(balm_ctx *c, double *buf, size_t count) {
   if (c->world <= 1 || !c->comm) return BALM_OK;
   const int rc = g_nccl.AllReduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
@@ -572,7 +604,15 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
     TRY(launch_assemble(c));
     CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
   }
-  TRY(allreduce_sum(c, c->H, (size_t)c->n * c->n + c->n + 1));
+  if (c->world > 1 && c->comm) {
+    const int n = c->n;
+    const size_t cnt = (size_t)n * (n + 1) / 2 + n + 1;
+    if (!c->Hpack) TRY(dev_alloc(&c->Hpack, cnt));
+    pack_lower_kernel<<<dim3((n + 256) / 256, n), 256, 0, c->stream>>>(c->H, c->Hpack, n);
+    TRY(allreduce_sum(c, c->Hpack, cnt));
+    unpack_lower_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), dim3(32, 32), 0, c->stream>>>(c->Hpack, c->H, n);
+    c->launches += 2;
+  }
   CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->scal, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   if (deferred) {
@@ -653,15 +693,32 @@ static int collect_solve(balm_ctx *c, double *q1, int *not_pd) {
   return BALM_OK;
 }
 
+// The backward-error check of the last solve failed (flags[4]: an indefinite H + uD factored without pivoting lost
+// digits): refine dx in fp64 with the same factors; if that does not bring the error down, the step counts as not_pd.
+// Returns 1 in *refined when dx changed (the caller re-applies the pose update).
+static int maybe_refine(balm_ctx *c, double *q1, int *not_pd, int *refined) {
+  *refined = 0;
+  if (c->h_flags[4] == 0 || *not_pd) return BALM_OK;
+  int still_bad = 0;
+  TRY(refine_solution(c, &still_bad));
+  *q1 = c->h_scal[1];
+  *refined = 1;
+  if (still_bad || !std::isfinite(*q1)) *not_pd = 1;
+  return BALM_OK;
+}
+
 static int solve_dev(balm_ctx *c, double u, double *q1, int *not_pd) {
   CUDA_TRY(cudaEventRecord(c->ev[9], c->stream));
   TRY(launch_ldlt_solve(c, u));
   CUDA_TRY(cudaEventRecord(c->ev[10], c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->h_scal + 1, c->scal + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->h_flags, c->flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  if (c->defer) return BALM_OK;  // collect_solve() after the iteration's synchronisation
+  CUDA_TRY(cudaMemcpyAsync(c->h_flags + 4, c->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (c->defer) return BALM_OK;  // collect_solve() / maybe_refine() after the iteration's synchronisation
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  return collect_solve(c, q1, not_pd);
+  TRY(collect_solve(c, q1, not_pd));
+  int refined = 0;
+  return maybe_refine(c, q1, not_pd, &refined);
 }
 
 extern "C" int balm_solve(balm_ctx *c, double u, double *dx, double *q1, int *not_pd) {
@@ -742,6 +799,12 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
     if (was_deferred) {
       TRY(collect_eval(c));
       TRY(collect_solve(c, &q1, &not_pd));
+      int refined = 0;
+      TRY(maybe_refine(c, &q1, &not_pd, &refined));
+      if (refined && !not_pd) {  // dx changed: the trial poses and their residual are recomputed (rare path, synchronous)
+        TRY(launch_pose_update(c, c->poses, c->dx, c->poses_trial));
+        TRY(residual_dev(c, c->poses_trial, &r2, hand_over));
+      }
     }
     if (calc_hess) r1 = c->h_scal[0];
     double q = r1 - r2;
@@ -844,6 +907,16 @@ extern "C" int balm_timer_end(balm_ctx *c, float *ms) {
   cudaEventDestroy(e);
   return BALM_OK;
 }
+// Debug aid (BALM_DAG_TRACE=1): timestamps of the last tile-DAG factorisation. out: 4*nt chain entries (step start,
+// mini-panel inputs ready, diagonal block ready, step published; ns) followed by 3 per CTA (start, end, tasks).
+extern "C" int balm_debug_dag_trace(balm_ctx *c, unsigned long long *out, int max_entries) {
+  if (!c || !out || !c->dag_trace) return BALM_ERR_INVALID;
+  const int nt = (c->n + BALM_NB - 1) / BALM_NB;
+  const int total = std::min(max_entries, 4 * nt + 8 * 1024);
+  CUDA_TRY(cudaMemcpy(out, c->dag_trace, sizeof(unsigned long long) * total, cudaMemcpyDeviceToHost));
+  return BALM_OK;
+}
+
 extern "C" int balm_device_views(balm_ctx *c, double **H_dev, double **g_dev) {
   if (!c) return BALM_ERR_INVALID;
   if (H_dev) *H_dev = c->H;

@@ -67,6 +67,13 @@ struct balm_ctx {
   double *Xinv = nullptr;                           // [panels][64*64] inverses of the unit-lower diagonal blocks
   double *dinv = nullptr;                           // [n] 1/d
   double *sol = nullptr;                            // [n] right-hand side / forward-substitution vector
+  double *dval = nullptr;                           // [n] d (the tile-DAG factorisation scales its operands with it)
+  double *rres = nullptr;                           // [n] residual b - A x of the last solve (backward-error check)
+  double *rdelta = nullptr;                         // [n] refinement correction
+  int *dag_flags = nullptr;                         // tile-DAG dependency counters: upd | pdone [nt*nt], xdone | rhs_cnt [nt]
+  bool solve_dag = true;                            // persistent tile-DAG factorisation (BALM_SOLVE_MULTIKERNEL=1: old path)
+  int dag_grid = 0, dag_near = 0;
+  unsigned long long *dag_trace = nullptr;          // BALM_DAG_TRACE: device timestamps of the last factorisation
   void *solve_graph = nullptr;                      // cudaGraphExec_t of the solve sequence
   int solve_launches = 0;
   double *scal = nullptr;                           // device scalars [32]: 0 r(eval) 1 q1 2 r(residual) 3 u 4..15 gauge
@@ -98,6 +105,7 @@ struct balm_ctx {
 
   // ---- multi-GPU ----
   void *comm = nullptr;
+  double *Hpack = nullptr;        // [n(n+1)/2 + n + 1] lower triangle of H | g | r: what the all-reduce carries
   int rank = 0, world = 1;
 
   // ---- instrumentation ----
@@ -264,6 +272,7 @@ int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1
 int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch);
 int launch_assemble(balm_ctx *c);
 int launch_ldlt_solve(balm_ctx *c, double u);
+int refine_solution(balm_ctx *c, int *still_bad);
 int launch_pose_update(balm_ctx *c, const double *poses_in, const double *dx, double *poses_out);
 int launch_gauge(balm_ctx *c, double *poses, int mode);
 int launch_synth(balm_ctx *c, int64_t n_voxels, int64_t first_voxel, int pts, double noise, double range,

@@ -12,6 +12,7 @@
 //
 // A is column-major n x n; only the lower triangle is read/written. Panel width NB = 64.
 #include <stdlib.h>
+#include <algorithm>
 #include "internal.cuh"
 #define TRY_LAUNCH(x) do { int _s = (x); if (_s != BALM_OK) return _s; } while (0)
 
@@ -371,6 +372,445 @@ __global__ void __launch_bounds__(256) ldl_update_kernel(double *A, const double
   }
 }
 
+
+// =====================================================================================================================
+// Persistent tile-DAG factorisation (default).  ONE cooperative launch factors the whole matrix; 64 x 64 tiles, the
+// dependencies between tile tasks are counters in global memory instead of kernel boundaries:
+//   chain CTA (block 0)  for k = 0 .. nt-1: D'(k) = [mini-panel L_{k,k-1} = A_{k,k-1} X_{k-1}^T d^-1, mini-update
+//                        A_kk -= L W^T, both in shared memory] + the 64 x 64 factorisation (diag_factor) + y_k.
+//                        The serial chain of the solve is these nt steps and nothing else.
+//   worker CTAs          P(r,k): L_rk = A_rk X_k^T d_k^-1, rhs_r -= L_rk y_k        (r >= k+2; row k+1 is the chain's)
+//                        U(r,c,k): A_rc -= L_rk d_k L_ck^T (fp64 tensor-core MMAs)  (r >= c > k, except (k+1,k+1))
+// Tasks are enumerated step-major, row by row (the rows next to the diagonal -- what the chain needs next -- first) and
+// dealt round-robin inside two groups: a few "near" CTAs take the rows within NEAR_ROWS of the diagonal, so that what
+// feeds the chain never queues behind far-away trailing updates; all other CTAs take the rest. Every CTA walks its tasks
+// in the global order and waits only for tasks that come earlier in that order, and all CTAs are co-resident
+// (cooperative launch), so the scheme cannot deadlock. Updates of one tile are applied in step order (counter upd[r][c]),
+// hence the result is bit-reproducible. W = L d is never stored: U scales its A-operand fragments by d on the fly.
+// Memory model: producers  stores -> __syncthreads -> thread 0: st.release.gpu(counter);
+//               consumers  thread 0: ld.acquire.gpu spin -> __syncthreads -> data through L2 (cp.async.cg / ld.global.cg).
+namespace dag {
+
+constexpr int T = 64;
+constexpr int LDT = T + 4;   // smem row pitch (doubles): conflict-free DMMA fragment loads, 16-byte aligned rows
+constexpr int NEAR_ROWS = 4; // rows k+2 .. k+1+NEAR_ROWS of step k go to the near group
+
+struct Args {
+  double *A;            // n x n column-major, lower triangle: in H + uD, out L (below the diagonal) and d (on it)
+  int n, nt;
+  double *Xinv;         // [nt][64*64] column-major inverses of the unit-lower diagonal blocks
+  double *dinv, *dval;  // [n] 1/d, d
+  double *sol;          // [n] running right-hand side (in: b)
+  double *ysol;         // [n] y = L^-1 b
+  int *flags;           // [0] bad pivot
+  int *upd;             // [nt*nt] number of updates applied to tile (r,c)
+  int *pdone;           // [nt*nt] L_rk final
+  int *xdone;           // [nt]    X_k, d_k, y_k published
+  int *rhs_cnt;         // [nt]    number of rhs updates applied to row block r
+  int near_ctas;        // CTAs 1 .. near_ctas form the near group
+  unsigned long long *trace;  // optional (BALM_DAG_TRACE): chain [nt][4] step timestamps, then per CTA [wait ns, busy ns, tasks]
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_ge(const int *p, int want) {  // called by ONE thread, followed by __syncthreads
+  while (ld_acquire(p) < want) __nanosleep(20);
+}
+__device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
+
+// dst[kk][rr] = A[(col0+kk)*n + row0+rr], zero outside the matrix (16-byte cp.async.cg pieces: through L2)
+__device__ __forceinline__ void tile_load(double *dst, const double *A, int n, int col0, int row0) {
+#pragma unroll
+  for (int it = 0; it < 8; it++) {
+    const int e = threadIdx.x + it * 256, kk = e >> 5, rr = (e & 31) * 2;
+    double *d = dst + kk * LDT + rr;
+    if (col0 + kk < n && row0 + rr < n) cp_async16(d, A + (size_t)(col0 + kk) * n + row0 + rr);
+    else *reinterpret_cast<double2 *>(d) = make_double2(0.0, 0.0);
+  }
+}
+// dst[kk][c] = Xcm[kk*64 + c] = X[c][kk]   (B operand of W = A_rk X^T)
+__device__ __forceinline__ void x_load(double *dst, const double *Xcm) {
+#pragma unroll
+  for (int it = 0; it < 8; it++) {
+    const int e = threadIdx.x + it * 256, kk = e >> 5, rr = (e & 31) * 2;
+    cp_async16(dst + kk * LDT + rr, Xcm + kk * T + rr);
+  }
+}
+__device__ __forceinline__ void cp_wait_all() {
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
+// acc (+)= sum_kk sA[kk][row] * scale[kk] * sB[kk][col]; 8 warps, warp tile 32 x 16, C fragment element (i,j,h):
+// row = wm*32 + i*8 + fr, col = wn*16 + j*8 + 2*fk + h
+__device__ __forceinline__ void tile_mma(double (&acc)[4][2][2], const double *sA, const double *sB, const double *scale) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 2, wn = warp & 3, fr = lane >> 2, fk = lane & 3;
+#pragma unroll
+  for (int kk = 0; kk < T; kk += 4) {
+    const double sc = scale ? scale[kk + fk] : 1.0;
+    double af[4], bf[2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) af[i] = sA[(kk + fk) * LDT + wm * 32 + i * 8 + fr] * sc;
+#pragma unroll
+    for (int j = 0; j < 2; j++) bf[j] = sB[(kk + fk) * LDT + wn * 16 + j * 8 + fr];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+  }
+}
+__device__ __forceinline__ void acc_zero(double (&acc)[4][2][2]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+}
+
+struct Prof { unsigned long long wait, load, mma, store, panel; };
+
+// ---- worker task U(r,c,k): A_rc -= L_rk d_k L_ck^T ----
+__device__ __forceinline__ void task_update(const Args &a, int r, int c, int k, double *t0, double *t1, double *vec,
+                                            Prof &pf) {
+  const int tid = threadIdx.x, nt = a.nt, n = a.n;
+  unsigned long long q0 = a.trace ? gtime() : 0ull;
+  // three counters, three threads of three different warps: the round trips overlap
+  if (tid == 0) wait_ge(a.pdone + r * nt + k, 1);
+  if (tid == 32) wait_ge(a.pdone + c * nt + k, 1);
+  if (tid == 64) wait_ge(a.upd + r * nt + c, k);
+  __syncthreads();
+  if (a.trace) { const unsigned long long q = gtime(); pf.wait += q - q0; q0 = q; }
+  tile_load(t0, a.A, n, k * T, r * T);
+  if (r != c) tile_load(t1, a.A, n, k * T, c * T);
+  if (tid < T) vec[tid] = (k * T + tid < n) ? ld_cg(a.dval + k * T + tid) : 0.0;
+  asm volatile("cp.async.commit_group;\n" ::);
+  // the C tile (read-modify-write) is requested while the operands are in flight
+  const int lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3, fr = lane >> 2, fk = lane & 3;
+  double cv[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int row = r * T + wm * 32 + i * 8 + fr, col = c * T + wn * 16 + j * 8 + 2 * fk + h;
+        cv[i][j][h] = (row < n && col < n && row >= col) ? ld_cg(a.A + (size_t)col * n + row) : 0.0;
+      }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  if (a.trace) { const unsigned long long q = gtime(); pf.load += q - q0; q0 = q; }
+  double acc[4][2][2];
+  acc_zero(acc);
+  tile_mma(acc, t0, r != c ? t1 : t0, vec);
+  if (a.trace) { const unsigned long long q = gtime(); pf.mma += q - q0; q0 = q; }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int row = r * T + wm * 32 + i * 8 + fr, col = c * T + wn * 16 + j * 8 + 2 * fk + h;
+        if (row < n && col < n && row >= col) a.A[(size_t)col * n + row] = cv[i][j][h] - acc[i][j][h];
+      }
+  __syncthreads();
+  if (tid == 0) { __threadfence(); st_release(a.upd + r * nt + c, k + 1); }
+  if (a.trace) { const unsigned long long q = gtime(); pf.store += q - q0; }
+}
+
+// W = A_rk X_k^T into registers, then staged as  sL[c][row] = W d^-1 (= L_rk, k-major: the A-operand layout) and,
+// if sW != null, sW[c][row] = W (the B-operand layout of L W^T). t0/t1: operand tiles (overwritten).
+__device__ __forceinline__ void panel_tile(const Args &a, int r, int k, double *t0, double *t1, double *sL, double *sW,
+                                           double *vdinv) {
+  const int tid = threadIdx.x;
+  tile_load(t0, a.A, a.n, k * T, r * T);
+  x_load(t1, a.Xinv + (size_t)k * T * T);
+  if (tid < T) vdinv[tid] = ld_cg(a.dinv + k * T + tid);  // column blocks k < nt-1 are full
+  cp_wait_all();
+  __syncthreads();
+  double acc[4][2][2];
+  acc_zero(acc);
+  tile_mma(acc, t0, t1, nullptr);
+  __syncthreads();  // every warp has read t0 / t1 (sL / sW may alias them)
+  const int lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3, fr = lane >> 2, fk = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int row = wm * 32 + i * 8 + fr, col = wn * 16 + j * 8 + 2 * fk + h;
+        sL[col * LDT + row] = acc[i][j][h] * vdinv[col];
+        if (sW) sW[col * LDT + row] = acc[i][j][h];
+      }
+  __syncthreads();
+}
+
+// ---- worker task P(r,k) ----
+__device__ __forceinline__ void task_panel(const Args &a, int r, int k, double *t0, double *t1, double *vec) {
+  const int tid = threadIdx.x, nt = a.nt, n = a.n;
+  if (tid == 0) wait_ge(a.xdone + k, 1);
+  if (tid == 32) wait_ge(a.upd + r * nt + k, k);
+  if (tid == 64) wait_ge(a.rhs_cnt + r, k);
+  __syncthreads();
+  double *vdinv = vec, *vy = vec + T;
+  if (tid >= T && tid < 2 * T) vy[tid - T] = ld_cg(a.ysol + k * T + tid - T);
+  panel_tile(a, r, k, t0, t1, /*sL=*/t0, nullptr, vdinv);
+  // L_rk back to the matrix (coalesced along rows) and the forward-substitution update of this row block
+#pragma unroll 4
+  for (int e = tid; e < T * T; e += 256) {
+    const int col = e >> 6, row = e & 63;
+    if (r * T + row < n) a.A[(size_t)(k * T + col) * n + r * T + row] = t0[col * LDT + row];
+  }
+  if (tid < T && r * T + tid < n) {
+    double s = 0.0;
+#pragma unroll 8
+    for (int cc = 0; cc < T; cc++) s += t0[cc * LDT + tid] * vy[cc];
+    a.sol[r * T + tid] = ld_cg(a.sol + r * T + tid) - s;
+  }
+  __syncthreads();
+  if (tid == 0) { __threadfence(); st_release(a.pdone + r * nt + k, 1); st_release(a.rhs_cnt + r, k + 1); }
+}
+
+// ---- the chain CTA ----
+__device__ __forceinline__ void chain(const Args &a, double *smem) {
+  double (*S)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem);
+  double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem + NB * (NB + 1));
+  double (*Wp)[17] = reinterpret_cast<double (*)[17]>(smem + 2 * NB * (NB + 1));
+  double (*col16)[16] = reinterpret_cast<double (*)[16]>(smem + 2 * NB * (NB + 1) + NB * 17);
+  double *bvec = smem + 2 * NB * (NB + 1) + NB * 17 + 32;
+  double *vec = bvec + NB;                                   // [2*T] dinv_k | y_k
+  double *t0 = smem + 2 * NB * (NB + 1) + NB * 17 + 32 + NB + 2 * T;  // 16-byte aligned (all terms even)
+  double *t1 = t0 + T * LDT;
+  double *t2 = t1 + T * LDT;
+  double *t3 = t2 + T * LDT;
+  const int tid = threadIdx.x, n = a.n, nt = a.nt;
+  const int lane = tid & 31, warp = tid >> 5, wm = warp >> 2, wn = warp & 3, fr = lane >> 2, fk = lane & 3;
+  for (int k = 0; k < nt; k++) {
+    const int j0 = k * T;
+    const int nbw = (n - j0 < T) ? n - j0 : T;
+    double accu[4][2][2];
+    acc_zero(accu);
+    double bloc = 0.0;  // threads < 64: this block's right-hand side entry
+    if (a.trace && tid == 0) a.trace[4 * k + 0] = gtime();
+    if (k > 0) {
+      // mini-panel of step k-1 for row block k: L_{k,k-1}, W_{k,k-1}; mini-update of A_kk and of b_k
+      if (tid == 0) wait_ge(a.upd + k * nt + (k - 1), k - 1);
+      if (tid == 32) wait_ge(a.rhs_cnt + k, k - 1);
+      if (a.trace && tid == 0) a.trace[4 * k + 1] = gtime();
+      __syncthreads();
+      if (tid >= T && tid < 2 * T) vec[tid] = ld_cg(a.ysol + (k - 1) * T + tid - T);
+      panel_tile(a, k, k - 1, t0, t1, /*sL=*/t2, /*sW=*/t3, vec);
+#pragma unroll 4
+      for (int e = tid; e < T * T; e += 256) {
+        const int col = e >> 6, row = e & 63;
+        if (row < nbw) a.A[(size_t)((k - 1) * T + col) * n + j0 + row] = t2[col * LDT + row];
+      }
+      if (tid < T) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int cc = 0; cc < T; cc++) s += t2[cc * LDT + tid] * vec[T + cc];
+        bloc = (tid < nbw) ? ld_cg(a.sol + j0 + tid) - s : 0.0;
+      }
+      tile_mma(accu, t2, t3, nullptr);  // L W^T
+      __syncthreads();
+      if (tid == 0) { __threadfence(); st_release(a.pdone + k * nt + (k - 1), 1); }
+      if (tid == 0) wait_ge(a.upd + k * nt + k, k - 1);
+      if (a.trace && tid == 0) a.trace[4 * k + 2] = gtime();
+      __syncthreads();
+    } else if (tid < T) {
+      bloc = (tid < nbw) ? a.sol[j0 + tid] : 0.0;
+    }
+    // the diagonal block (lower triangle; rows/cols of a short last block act as identity), minus the mini-update
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+      const int e = tid + it * 256, r = e & (NB - 1), c = e >> 6;
+      double v = (r == c) ? 1.0 : 0.0;
+      if (r < nbw && c < nbw && r >= c) v = ld_cg(a.A + (size_t)(j0 + c) * n + j0 + r);
+      S[r][c] = v;
+      Xs[r][c] = 0.0;
+    }
+    if (tid < NB) bvec[tid] = bloc;
+    __syncthreads();
+    if (k > 0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int r = wm * 32 + i * 8 + fr, c = wn * 16 + j * 8 + 2 * fk + h;
+            if (r < nbw && c < nbw && r >= c) S[r][c] -= accu[i][j][h];
+          }
+      __syncthreads();
+    }
+    const bool bad = diag_factor(S, Xs, Wp, col16);
+    if (bad && tid == 0) atomicOr(&a.flags[0], 1);
+    double *Xcm = a.Xinv + (size_t)k * NB * NB;
+#pragma unroll 4
+    for (int e = tid; e < NB * NB; e += 256) {
+      const int r = e & (NB - 1), c = e >> 6;
+      if (r < nbw && c < nbw && r >= c) a.A[(size_t)(j0 + c) * n + j0 + r] = S[r][c];
+      Xcm[c * NB + r] = (r >= c) ? Xs[r][c] : 0.0;
+    }
+    if (tid < nbw) { a.dinv[j0 + tid] = 1.0 / S[tid][tid]; a.dval[j0 + tid] = S[tid][tid]; }
+    if (tid < NB) {
+      double sacc = 0.0;
+      for (int c = 0; c <= tid; c++) sacc += Xs[tid][c] * bvec[c];
+      if (tid < nbw) a.ysol[j0 + tid] = sacc;
+    }
+    __syncthreads();
+    if (tid == 0) { __threadfence(); st_release(a.xdone + k, 1); }
+    if (a.trace && tid == 0) a.trace[4 * k + 3] = gtime();
+  }
+}
+
+constexpr int SMEM_DOUBLES = 2 * NB * (NB + 1) + NB * 17 + 32 + NB + 2 * T + 4 * T * LDT;
+
+__global__ void __launch_bounds__(256, 1) ldl_dag_kernel(Args a) {
+  extern __shared__ __align__(16) double dyn_smem[];
+  if (blockIdx.x == 0) { chain(a, dyn_smem); return; }
+  const int nt = a.nt, W = gridDim.x;
+  if (nt < 2) return;
+  // group of this CTA, its index and size inside the group
+  const bool near = (int)blockIdx.x <= a.near_ctas;
+  const int gsize = near ? a.near_ctas : W - 1 - a.near_ctas;
+  const int gidx = near ? blockIdx.x - 1 : blockIdx.x - 1 - a.near_ctas;
+  if (gsize <= 0) return;
+  double *t0 = dyn_smem, *t1 = dyn_smem + T * LDT, *vec = dyn_smem + 2 * T * LDT;
+  unsigned long long t_begin = a.trace ? gtime() : 0ull, n_tasks = 0;
+  Prof pf{0, 0, 0, 0, 0};
+  const bool split = a.near_ctas > 0 && W - 1 - a.near_ctas > 0;  // two groups; otherwise one group takes every row
+  // `next`: position (in the group's running task count) of this CTA's next task, relative to the current list.
+  // Every list below is walked with a stride of gsize from there, so a CTA touches only its own tasks (the lists of a
+  // 47-step factorisation hold 18 000 tasks; enumerating all of them in every CTA cost more than executing its share).
+  int next = gidx;
+  for (int k = 0; k + 1 < nt; k++) {
+    // Worker tasks of step k: rows r = k+2 .. nt-1 (row k+1 is the chain's): P(r,k), then U(r,c,k) for c = k+1 .. r.
+    const int r_split = split ? (k + 2 + NEAR_ROWS < nt ? k + 2 + NEAR_ROWS : nt) : nt;  // rows below r_split: near group
+    if (near || !split) {
+      // near group: row by row (what the chain needs next first); P and the U tasks of a row are consecutive
+      int base = 0;  // tasks of this list before row r
+      for (int r = k + 2; r < r_split; r++) {
+        const int ntask = 1 + (r - k);
+        for (; next < base + ntask; next += gsize) {
+          const int t = next - base;
+          if (t == 0) task_panel(a, r, k, t0, t1, vec);
+          else task_update(a, r, k + t, k, t0, t1, vec, pf);
+          n_tasks++;
+        }
+        base += ntask;
+      }
+      next -= base;
+    }
+    if (!near && split) {
+      // far group: ALL panel tasks of the step first, then the updates -- an update dealt in the same round as the
+      // panel task it depends on would idle its CTA for the length of that task
+      const int np = nt - r_split;
+      for (; next < np; next += gsize) {
+        const unsigned long long q0 = a.trace ? gtime() : 0ull;
+        task_panel(a, r_split + next, k, t0, t1, vec);
+        if (a.trace) pf.panel += gtime() - q0;
+        n_tasks++;
+      }
+      next -= np;
+      int base = 0;
+      for (int r = r_split; r < nt; r++) {
+        const int ntask = r - k;  // c = k+1 .. r
+        for (; next < base + ntask; next += gsize) {
+          task_update(a, r, k + 1 + (next - base), k, t0, t1, vec, pf);
+          n_tasks++;
+        }
+        base += ntask;
+      }
+      next -= base;
+    }
+  }
+  if (a.trace && threadIdx.x == 0) {
+    unsigned long long *o = a.trace + 4 * nt + 8 * blockIdx.x;
+    o[0] = t_begin; o[1] = gtime(); o[2] = n_tasks;
+    o[3] = pf.wait; o[4] = pf.load; o[5] = pf.mma; o[6] = pf.store; o[7] = pf.panel;
+  }
+}
+
+}  // namespace dag
+
+
+// ---- backward error of the computed step, and iterative refinement -----------------------------------------------
+// The factorisation does not pivot (Eigen's LDLT, bavoxel.hpp:1114, pivots on the diagonal). For the positive-definite
+// systems of the accepted-step regime that is backward stable; for an INDEFINITE H + uD (strongly perturbed start, tiny
+// u) element growth can cost digits. So every solve is followed by the componentwise backward error
+//     omega = max_i |b - A x|_i / (|A| |x| + |b|)_i ,   A = H + u diag(H), b = -g      (Oettli-Prager)
+// computed in fp64 from H itself (one warp per row). omega > tol raises flags[4]; the host then runs fp64 iterative
+// refinement with the same factors (refine_solution) -- at most three rounds -- and, if omega still does not fall below
+// the tolerance, reports the step as not_pd (rejected, u *= v), never a silently inaccurate dx.
+__global__ void __launch_bounds__(256) solve_residual_kernel(const double *H, const double *g, const double *x, int n,
+                                                             const double *u_dev, double tol, double *rres, int *flags,
+                                                             double *omega_out) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const double u = *u_dev;
+  double s = 0.0, sa = 0.0;
+  for (int j = lane; j < n; j += 32) {  // H symmetric: row `row` = column `row`, contiguous
+    double h = H[(size_t)row * n + j];
+    if (j == row) h += u * h;
+    const double t = h * x[j];
+    s += t;
+    sa += fabs(t);
+  }
+  s = warp_sum(s);
+  sa = warp_sum(sa);
+  if (lane == 0) {
+    const double b = -g[row], r = b - s, den = sa + fabs(b);
+    rres[row] = r;
+    const double om = den > 0.0 ? fabs(r) / den : 0.0;
+    if (!(om <= tol)) atomicOr(&flags[4], 1);
+    atomicMax(reinterpret_cast<unsigned long long *>(omega_out), (unsigned long long)__double_as_longlong(om));
+  }
+}
+
+// Forward substitution for a fresh right-hand side (refinement only; the first solve fuses it into the factorisation):
+// one 64-row block per launch: y_j = X_j b_j, rows below -= L21 y_j.
+__global__ void __launch_bounds__(256) ldl_fwd_block_kernel(const double *A, int n, int j0, int nbw, const double *Xcm,
+                                                            double *sol, double *ysol) {
+  __shared__ double b[NB], y[NB];
+  const int tid = threadIdx.x;
+  if (tid < NB) b[tid] = tid < nbw ? sol[j0 + tid] : 0.0;
+  __syncthreads();
+  if (tid < NB) {
+    double sacc = 0.0;
+    for (int c = 0; c <= tid; c++) sacc += Xcm[c * NB + tid] * b[c];  // X[tid][c]
+    y[tid] = sacc;
+    if (blockIdx.x == 0 && tid < nbw) ysol[j0 + tid] = sacc;
+  }
+  __syncthreads();
+  const int i = j0 + nbw + blockIdx.x * 256 + tid;
+  if (i < n) {
+    double s = 0.0;
+    for (int c = 0; c < nbw; c++) s += A[(size_t)(j0 + c) * n + i] * y[c];
+    sol[i] -= s;
+  }
+}
+
+__global__ void axpy_kernel(double *x, const double *d, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] += d[i];
+}
+__global__ void copy_kernel(double *dst, const double *src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
 // rhs = -g (start of the forward substitution, fused into the factorisation kernels)
 __global__ void rhs_init_kernel(const double *g, double *sol, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -571,23 +1011,142 @@ static int enqueue_solve(balm_ctx *c) {
   return BALM_OK;
 }
 
+
+constexpr double SOLVE_OMEGA_TOL = 1e-12;  // componentwise backward error accepted without refinement
+
+// omega of the current c->dx (+ the residual vector in c->rres); flags[4] raised when omega > tol. scal[20] = omega.
+static int enqueue_solve_check(balm_ctx *c) {
+  const int n = c->n;
+  CUDA_TRY(cudaMemsetAsync(c->scal + 20, 0, sizeof(double), c->stream));
+  solve_residual_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(c->H, c->g, c->dx, n, c->scal + 3, SOLVE_OMEGA_TOL, c->rres,
+                                                            c->flags, c->scal + 20);
+  c->launches += 1;
+  return BALM_OK;
+}
+
+static int enqueue_back_substitution(balm_ctx *c, const double *rhs_g, double *x_out, bool with_q1);
+
+// fp64 iterative refinement of c->dx with the factors left in c->A / c->Xinv / c->dinv (host-driven, rare path: the
+// backward-error check of the last solve raised flags[4]). Returns via *still_bad whether omega stayed above the tolerance.
+int refine_solution(balm_ctx *c, int *still_bad) {
+  const int n = c->n;
+  cudaStream_t st = c->stream;
+  *still_bad = 1;
+  for (int round = 0; round < 3; round++) {
+    // solve A delta = r with the existing factors: forward (block by block), scale, backward
+    copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->sol, c->rres, n);
+    int launches = 1;
+    for (int j0 = 0, pi = 0; j0 < n; j0 += NB, pi++) {
+      const int nbw = (n - j0 < NB) ? n - j0 : NB;
+      const int m = n - j0 - nbw;
+      ldl_fwd_block_kernel<<<m > 0 ? (m + 255) / 256 : 1, 256, 0, st>>>(c->A, n, j0, nbw, c->Xinv + (size_t)pi * NB * NB,
+                                                                        c->sol, c->ysol);
+      launches++;
+    }
+    c->launches += launches;
+    TRY_LAUNCH(enqueue_back_substitution(c, c->g, c->rdelta, false));
+    axpy_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->dx, c->rdelta, n);
+    q1_kernel<<<1, 1024, 0, st>>>(c->dx, c->g, c->dvec, n, c->scal + 3, c->scal);
+    c->launches += 2;
+    CUDA_TRY(cudaMemsetAsync(c->flags + 4, 0, sizeof(int), st));
+    TRY_LAUNCH(enqueue_solve_check(c));
+    CUDA_TRY(cudaMemcpyAsync(c->h_flags + 4, c->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_scal + 1, c->scal + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    c->tm.refinements += 1;
+    if (c->h_flags[4] == 0) { *still_bad = 0; break; }
+  }
+  return BALM_OK;
+}
+
+// Everything of the solve that follows the factorisation: w = d^-1 y, grouped backward substitution, q1.
+static int enqueue_back_substitution(balm_ctx *c, const double *rhs_g, double *x_out, bool with_q1) {
+  const int n = c->n;
+  cudaStream_t st = c->stream;
+  scale_rhs_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->sol, c->ysol, c->dinv, n);
+  int launches = 1;
+  const int npan = (n + NB - 1) / NB;
+  for (int hi = npan - 1; hi >= 0; hi -= BACK_GROUP) {
+    const int lo = hi - BACK_GROUP + 1 > 0 ? hi - BACK_GROUP + 1 : 0;
+    const int g_lo = lo * NB;
+    const int g_hi = (hi + 1) * NB < n ? (hi + 1) * NB : n;
+    const int blocks = g_lo > 0 ? (g_lo + 31) / 32 : 1;
+    ldl_back_kernel<<<blocks, 256, 0, st>>>(c->A, n, g_lo, g_hi - g_lo, c->Xinv + (size_t)lo * NB * NB, c->sol, x_out);
+    launches++;
+  }
+  if (with_q1) {
+    q1_kernel<<<1, 1024, 0, st>>>(x_out, rhs_g, c->dvec, n, c->scal + 3, c->scal);
+    launches++;
+  }
+  c->launches += launches;
+  return BALM_OK;
+}
+
+// Persistent tile-DAG path: damp/copy + rhs, ONE cooperative launch for the factorisation and forward substitution,
+// then the grouped backward substitution, q1 and the backward-error check.
+static int enqueue_solve_dag(balm_ctx *c) {
+  const int n = c->n, nt = (n + NB - 1) / NB;
+  cudaStream_t st = c->stream;
+  dim3 g1((n + 255) / 256, n);
+  damp_copy_kernel<<<g1, 256, 0, st>>>(c->H, c->A, c->dvec, n, c->scal + 3);
+  rhs_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(c->g, c->sol, n);
+  CUDA_TRY(cudaMemsetAsync(c->dag_flags, 0, sizeof(int) * (2 * (size_t)nt * nt + 2 * nt), st));
+  dag::Args a;
+  a.A = c->A; a.n = n; a.nt = nt; a.Xinv = c->Xinv; a.dinv = c->dinv; a.dval = c->dval; a.sol = c->sol; a.ysol = c->ysol;
+  a.flags = c->flags; a.upd = c->dag_flags; a.pdone = c->dag_flags + (size_t)nt * nt;
+  a.xdone = c->dag_flags + 2 * (size_t)nt * nt; a.rhs_cnt = a.xdone + nt;
+  int grid = nt < 2 ? 1 : c->dag_grid;
+  const int workers = grid - 1;
+  a.near_ctas = workers >= 16 ? c->dag_near : 0;
+  a.trace = c->dag_trace;
+  void *params[] = {&a};
+  CUDA_TRY(cudaLaunchCooperativeKernel((const void *)dag::ldl_dag_kernel, dim3(grid), dim3(256), params,
+                                       dag::SMEM_DOUBLES * sizeof(double), st));
+  c->launches += 3;
+  return enqueue_back_substitution(c, c->g, c->dx, true);
+}
+
 int launch_ldlt_solve(balm_ctx *c, double u) {
   const int n = c->n;
   if (!c->Xinv) {
     const int npan = (n + NB - 1) / NB;
     CUDA_TRY(cudaMalloc((void **)&c->Xinv, sizeof(double) * (size_t)npan * NB * NB));
     CUDA_TRY(cudaMalloc((void **)&c->dinv, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc((void **)&c->dval, sizeof(double) * n));
     CUDA_TRY(cudaMalloc((void **)&c->sol, sizeof(double) * n));
     CUDA_TRY(cudaMalloc((void **)&c->ysol, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc((void **)&c->rres, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc((void **)&c->rdelta, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc((void **)&c->dag_flags, sizeof(int) * (2 * (size_t)npan * npan + 2 * npan)));
     c->solve_lookahead = getenv("BALM_NO_LOOKAHEAD") == nullptr;
+    // the persistent factorisation needs every CTA resident at once: one CTA per SM (216 KB of shared memory each)
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dag::ldl_dag_kernel, 256,
+                                                           dag::SMEM_DOUBLES * sizeof(double)));
+    c->solve_dag = per_sm >= 1 && getenv("BALM_SOLVE_MULTIKERNEL") == nullptr;
+    c->dag_grid = c->sm_count;
+    if (const char *e = getenv("BALM_DAG_GRID")) c->dag_grid = std::max(2, std::min(atoi(e), c->sm_count));
+    if (getenv("BALM_DAG_TRACE")) {
+      CUDA_TRY(cudaMalloc((void **)&c->dag_trace, sizeof(unsigned long long) * (4 * (size_t)npan + 8 * 1024)));
+      CUDA_TRY(cudaMemset(c->dag_trace, 0, sizeof(unsigned long long) * (4 * (size_t)npan + 8 * 1024)));
+    }
+    c->dag_near = 8;
+    if (const char *e = getenv("BALM_DAG_NEAR")) c->dag_near = std::max(0, std::min(atoi(e), c->dag_grid - 2));
   }
   c->h_scal[3] = u;  // pinned; the kernels read the damping factor from device memory so the graph is reusable
   CUDA_TRY(cudaMemcpyAsync(c->scal + 3, c->h_scal + 3, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(cudaMemsetAsync(c->flags, 0, sizeof(int) * 4, c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->flags, 0, sizeof(int) * 8, c->stream));
+  if (c->solve_dag) {
+    TRY_LAUNCH(enqueue_solve_dag(c));
+    TRY_LAUNCH(enqueue_solve_check(c));
+    CUDA_TRY(cudaGetLastError());
+    return BALM_OK;
+  }
   static const bool use_graph = getenv("BALM_NO_GRAPH") == nullptr;
   if (!use_graph) {
     TRY_LAUNCH(enqueue_solve(c));
     c->launches += c->solve_launches;
+    TRY_LAUNCH(enqueue_solve_check(c));
     CUDA_TRY(cudaGetLastError());
     return BALM_OK;
   }
@@ -602,6 +1161,7 @@ int launch_ldlt_solve(balm_ctx *c, double u) {
   }
   CUDA_TRY(cudaGraphLaunch((cudaGraphExec_t)c->solve_graph, c->stream));
   c->launches += c->solve_launches;
+  TRY_LAUNCH(enqueue_solve_check(c));
   return BALM_OK;
 }
 
@@ -627,5 +1187,7 @@ int ldlt_setup() {
   CUDA_TRY(cudaFuncSetAttribute(ldl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 USTAGE * (int)sizeof(double)));
   CUDA_TRY(cudaFuncSetAttribute(ldl_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(dag::ldl_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dag::SMEM_DOUBLES * (int)sizeof(double)));
   return BALM_OK;
 }

@@ -78,6 +78,7 @@ typedef struct {
   int single_sweeps; /* tensor path: evaluations whose one fused observation sweep (column scales speculated from the
                         previous evaluation) was accepted ... */
   int redone_sweeps; /* ... and those whose scales failed the check, so the digit-plane sweep ran again */
+  int refinements;   /* solves whose backward-error check asked for fp64 iterative refinement (indefinite H + uD) */
   int n_stats;       /* evaluations that ran the per-voxel eigen pass themselves (ms_stats sums only these): inside
                         balm_damping_iter the residual pass of the previous step usually hands its results over */
 } balm_timings;
@@ -146,6 +147,9 @@ int balm_sync(balm_ctx *ctx);
 /* CUDA-event bracket on the ctx stream: begin records, end records + synchronises and returns elapsed ms. */
 int balm_timer_begin(balm_ctx *ctx);
 int balm_timer_end(balm_ctx *ctx, float *ms);
+/* Debug aid: with BALM_DAG_TRACE=1 in the environment, device timestamps (ns) of the last factorisation: 4 per 64-column
+ * step of the chain, then 3 per CTA (start, end, tasks executed). */
+int balm_debug_dag_trace(balm_ctx *ctx, unsigned long long *out, int max_entries);
 /* Device pointers of the last evaluation's H (n*n col-major), g (n) -- for zero-copy consumers. */
 int balm_device_views(balm_ctx *ctx, double **H_dev, double **g_dev);
 

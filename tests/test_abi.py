@@ -33,7 +33,7 @@ def test_fails_loudly_without_gpu():
 
 def test_struct_layouts_match_header():
     from balm_b200 import _lib
-    assert C.sizeof(_lib.LmOpts) == 56 and C.sizeof(_lib.Trace) == 64 and C.sizeof(_lib.Timings) == 68
+    assert C.sizeof(_lib.LmOpts) == 56 and C.sizeof(_lib.Trace) == 64 and C.sizeof(_lib.Timings) == 72
 
 
 def test_product_does_not_import_oracle():

@@ -74,7 +74,9 @@ def test_tensor_single_sweep_speculation(drop, monkeypatch):
     evaluation and ONE observation sweep writes the digit planes; a device-side check either accepts that or re-runs
     the digit sweep with fresh scales. The public evaluate never speculates (pure function of its arguments)."""
     sc = scenes.make_scene(n_poses=24, n_planes=150, seed=33, drop=drop)
-    kw = dict(max_iter=5, force_hess=True, rel_tol=-1.0)
+    # 4 iterations: all of them are genuine descent steps. (A 5th would sit at the converged cost, where r1 - r2 is pure
+    # rounding and its SIGN -- the accept flag -- is a coin flip between two arithmetically different paths.)
+    kw = dict(max_iter=4, force_hess=True, rel_tol=-1.0)
 
     def run():
         c = _ctx(sc, 1)
@@ -90,17 +92,17 @@ def test_tensor_single_sweep_speculation(drop, monkeypatch):
 
     monkeypatch.setenv("BALM_NO_SPEC", "1")
     p_two, t_two, tm = run()                                   # every evaluation sweeps twice
-    assert tm["n_eval"] == 5 and tm["single_sweeps"] == 0 and tm["redone_sweeps"] == 0
+    assert tm["n_eval"] == 4 and tm["single_sweeps"] == 0 and tm["redone_sweeps"] == 0
     monkeypatch.delenv("BALM_NO_SPEC")
     p_one, t_one, tm = run()
-    assert tm["n_eval"] == 5 and tm["single_sweeps"] + tm["redone_sweeps"] == 4 and tm["single_sweeps"] >= 1
+    assert tm["n_eval"] == 4 and tm["single_sweeps"] + tm["redone_sweeps"] == 3 and tm["single_sweeps"] >= 1
     assert [x[2] for x in t_one] == [x[2] for x in t_two]
     rot, tra = _pose_err(p_one, p_two)
     assert rot <= 1e-8 and tra <= 1e-8                         # scales differ by powers of two at most -> rounding only
     for skew in (4, -9):   # adopted scales 16x too large (digits overflow) / 512x too small (precision lost)
         monkeypatch.setenv("BALM_TC_SPEC_SKEW", str(skew))
         p_bad, t_bad, tm = run()
-        assert tm["single_sweeps"] == 0 and tm["redone_sweeps"] == 4, (skew, tm)
+        assert tm["single_sweeps"] == 0 and tm["redone_sweeps"] == 3, (skew, tm)
         # every speculation rejected -> the digit sweep re-ran with fresh scales -> the two-sweep result (the
         # accumulators come from a different instantiation of the sweep kernel, hence "to rounding", not "same bits")
         assert np.abs(p_bad - p_two).max() <= 1e-12

@@ -130,12 +130,18 @@ def test_indefinite_damped_system_vs_pivoted_ldlt():
         A = H + u * np.diag(np.diag(H))
         lam = np.linalg.eigvalsh(A)
         seen_indefinite += lam[0] < 0
+        cond = np.abs(lam).max() / np.abs(lam).min()
         dxo, zp = orc.ldlt_solve(A, -g)
         dx, q1, bad = c.solve(u)
-        relres = np.linalg.norm(A @ dx + g) / np.linalg.norm(g)
+        relres = np.linalg.norm(A @ dx + g) / (np.linalg.norm(A, 2) * np.linalg.norm(dx) + np.linalg.norm(g))
+        relres_o = np.linalg.norm(A @ dxo + g) / (np.linalg.norm(A, 2) * np.linalg.norm(dxo) + np.linalg.norm(g))
         if not bad:
-            assert np.abs(dx - dxo).max() <= 1e-8 * max(1.0, np.abs(dxo).max()), (u, np.abs(dx - dxo).max())
-            assert relres <= 1e-9, (u, relres)
+            # backward error at rounding level -- as good as the pivoted factorisation's ...
+            assert relres <= max(1e-14, 10 * relres_o), (u, relres, relres_o)
+            # ... hence the two solutions agree to what the conditioning of H + uD allows (two backward-stable solves of
+            # a system with condition number `cond` differ by O(cond * eps); here cond ~ 1e8: the gauge directions are
+            # held by the tiny damping only)
+            assert np.abs(dx - dxo).max() <= 20 * cond * 2.3e-16 * np.abs(dxo).max(), (u, cond, np.abs(dx - dxo).max())
             assert abs(q1 - 0.5 * dx @ (u * np.diag(H) * dx - g)) <= 1e-9 * abs(q1)
     assert seen_indefinite >= 1, "the scene was meant to produce an indefinite damped matrix"
     # and inside the LM loop: the same accept/reject sequence as the oracle from this start (rejections included)
