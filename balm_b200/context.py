@@ -118,6 +118,17 @@ class Context:
                    recomputed_hess=bool(t.recomputed_hess), not_pd=bool(t.not_pd)) for t in trace[:n_it.value]]
         return poses, tr, (per_iter[:n_it.value] if want_per_iter else None)
 
+    def pose_covariance(self, poses12, point_noise=0.0, c_cov=None, include_fix=False, want_raw=True, want_cov=True):
+        """left_jacobian_point / multi_second / H^-1 Rcov H^-T (BAs_left.hpp:342-473, 995-1023, 1089-1096).
+        -> (Rcov_raw, Rcov); c_cov: K x 9 x 9 per-observation cluster covariances, or None for isotropic point noise."""
+        poses12 = np.ascontiguousarray(poses12, dtype=np.float64)
+        cc = None if c_cov is None else np.ascontiguousarray(c_cov, dtype=np.float64).reshape(-1, 81)
+        raw = np.zeros((self.n, self.n), order="F") if want_raw else None
+        cov = np.zeros((self.n, self.n), order="F") if want_cov else None
+        L.check(L.lib().balm_pose_covariance(self._h, _p(poses12), _p(cc), float(point_noise), int(include_fix), _p(raw),
+                                             _p(cov)))
+        return raw, cov
+
     # ---- multi-GPU ----
     @staticmethod
     def comm_unique_id():

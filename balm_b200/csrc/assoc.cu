@@ -402,3 +402,76 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   *K_out = K;
   return BALM_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pose-major observation lists of a sparse co-visibility problem (the reference walks a voxel's win_size slots and
+// skips the empty ones, bavoxel.hpp:332,365-366,404-408; here the observation sweep runs lane = pose and needs, per pose,
+// the list of its observations in ascending voxel order). Built on the device: stable radix sort of the observation
+// indices by pose (CSR order is voxel-major, so a stable sort leaves every pose's list voxel-ascending), plus the
+// voxel of every observation. planes_host: per-pose counts (already on the host for the >= 20 planes guard).
+namespace {
+__global__ void obs_voxel_kernel(const long long *row_ptr, int64_t M, int *vox_of_obs) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= M) return;
+  for (long long s = row_ptr[v]; s < row_ptr[v + 1]; s++) vox_of_obs[s] = (int)v;
+}
+__global__ void gather_int_kernel(const int *src, const int *idx, int *dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+// one thread per pose: [lo, hi) = the part of its list whose voxels lie in [v0, v1)
+__global__ void csc_batch_kernel(const int *csc_ptr, const int *csc_vox, int N, int v0, int v1, int *lo, int *hi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int b = csc_ptr[i], e = csc_ptr[i + 1];
+  int l = b, h = e;
+  while (l < h) { const int m = (l + h) >> 1; if (csc_vox[m] < v0) l = m + 1; else h = m; }
+  lo[i] = l;
+  h = e;
+  while (l < h) { const int m = (l + h) >> 1; if (csc_vox[m] < v1) l = m + 1; else h = m; }
+  hi[i] = l;
+}
+}  // namespace
+
+int build_pose_major_lists(balm_ctx *c, const int *planes_host) {
+  const int N = c->N;
+  const int64_t K = c->K, M = c->M;
+  cudaStream_t st = c->stream;
+  ScratchPool pool;
+  std::vector<int> ptr((size_t)N + 1, 0);
+  for (int i = 0; i < N; i++) ptr[i + 1] = ptr[i] + planes_host[i];
+  c->csc_max_len = 0;
+  for (int i = 0; i < N; i++) c->csc_max_len = std::max(c->csc_max_len, planes_host[i]);
+  CUDA_TRY(cudaMalloc((void **)&c->csc_ptr, sizeof(int) * ((size_t)N + 1)));
+  CUDA_TRY(cudaMalloc((void **)&c->csc_obs, sizeof(int) * (size_t)K));
+  CUDA_TRY(cudaMalloc((void **)&c->csc_vox, sizeof(int) * (size_t)K));
+  CUDA_TRY(cudaMalloc((void **)&c->csc_lo, sizeof(int) * (size_t)N));
+  CUDA_TRY(cudaMalloc((void **)&c->csc_hi, sizeof(int) * (size_t)N));
+  CUDA_TRY(cudaMemcpyAsync(c->csc_ptr, ptr.data(), sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, st));
+  int *vox = nullptr, *idx = nullptr, *keys = nullptr, *keys2 = nullptr;
+  ATRY(pool.get(&vox, (size_t)K)); ATRY(pool.get(&idx, (size_t)K)); ATRY(pool.get(&keys, (size_t)K)); ATRY(pool.get(&keys2, (size_t)K));
+  obs_voxel_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(c->row_ptr, M, vox);
+  iota_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(idx, K);
+  CUDA_TRY(cudaMemcpyAsync(keys, c->pose_idx, sizeof(int) * (size_t)K, cudaMemcpyDeviceToDevice, st));
+  int bits = 1;
+  while ((1 << bits) < N) bits++;
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, idx, c->csc_obs, (int)K, 0, bits, st);
+  char *tmp = nullptr;
+  ATRY(pool.get(&tmp, tb));
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, idx, c->csc_obs, (int)K, 0, bits, st));
+  gather_int_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(vox, c->csc_obs, c->csc_vox, K);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 4;
+  return launch_csc_batch(c, 0, M);
+}
+
+int launch_csc_batch(balm_ctx *c, int64_t v0, int64_t v1) {
+  if (c->dense || !c->csc_ptr) return BALM_OK;
+  csc_batch_kernel<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->csc_ptr, c->csc_vox, c->N, (int)v0, (int)v1, c->csc_lo, c->csc_hi);
+  c->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return BALM_OK;
+}

@@ -60,7 +60,8 @@ static int dev_alloc(T **p, size_t count) {
 
 static void free_problem(balm_ctx *c) {
   cudaFree(c->obs); cudaFree(c->pose_idx); cudaFree(c->row_ptr); cudaFree(c->coe); cudaFree(c->fix);
-  cudaFree(c->csc_ptr); cudaFree(c->csc_obs); cudaFree(c->csc_vox);
+  cudaFree(c->csc_ptr); cudaFree(c->csc_obs); cudaFree(c->csc_vox); cudaFree(c->csc_lo); cudaFree(c->csc_hi);
+  c->csc_lo = c->csc_hi = nullptr;
   c->obs = nullptr; c->pose_idx = nullptr; c->row_ptr = nullptr; c->coe = nullptr; c->fix = nullptr;
   c->csc_ptr = c->csc_obs = c->csc_vox = nullptr;
   cudaFree(c->vsums); c->vsums = nullptr;
@@ -77,8 +78,8 @@ static int alloc_problem_arrays(balm_ctx *c, int64_t M, int64_t K, bool with_fix
   c->reuse_ws = c->obs && c->stats && c->M == M && c->K == K && (c->fix != nullptr) == with_fix &&
                 !getenv("BALM_NO_BUFFER_REUSE");
   if (c->reuse_ws) {
-    cudaFree(c->csc_ptr); cudaFree(c->csc_obs); cudaFree(c->csc_vox);
-    c->csc_ptr = c->csc_obs = c->csc_vox = nullptr;
+    cudaFree(c->csc_ptr); cudaFree(c->csc_obs); cudaFree(c->csc_vox); cudaFree(c->csc_lo); cudaFree(c->csc_hi);
+    c->csc_ptr = c->csc_obs = c->csc_vox = c->csc_lo = c->csc_hi = nullptr;
     return BALM_OK;
   }
   free_problem(c);
@@ -96,10 +97,6 @@ static int alloc_problem_arrays(balm_ctx *c, int64_t M, int64_t K, bool with_fix
 static int alloc_workspaces(balm_ctx *c) {
   if (c->reuse_ws) {  // same shape: batch size, split counts, tensor maps and digit-plane buffers are all unchanged
     c->reuse_ws = false;
-    if (!c->dense && c->VB < c->M) {
-      balm_set_error("sparse co-visibility problems must fit one evaluation batch");
-      return BALM_ERR_UNSUPPORTED;
-    }
     tensor_syrk_new_problem(c);
     return BALM_OK;
   }
@@ -108,10 +105,6 @@ static int alloc_workspaces(balm_ctx *c) {
   int64_t vb = (int64_t)(g_budget / ((size_t)3 * c->ldg * sizeof(double)));
   if (vb > c->M) vb = c->M;
   if (vb < 1) vb = 1;
-  if (!c->dense && vb < c->M) {
-    balm_set_error("sparse co-visibility problems must fit one evaluation batch");
-    return BALM_ERR_UNSUPPORTED;
-  }
   c->VB = vb;
   TRY(dev_alloc(&c->stats, (size_t)vb * BALM_STATS_STRIDE));
   if (vb == c->M && !getenv("BALM_NO_STATS_CACHE")) TRY(dev_alloc(&c->stats_trial, (size_t)vb * BALM_STATS_STRIDE));
@@ -184,6 +177,7 @@ extern "C" int balm_create(balm_ctx **out, int n_poses, int device, int precisio
   TRY(factor_kernels_setup());
   TRY(syrk_f64_setup());
   TRY(ldlt_setup());
+  TRY(covariance_setup());
   const size_t n = c->n;
   TRY(dev_alloc(&c->poses, 12 * (size_t)c->N));
   TRY(dev_alloc(&c->poses_trial, 12 * (size_t)c->N));
@@ -286,30 +280,7 @@ static int finish_registration(balm_ctx *c) {
   c->max_k = h_out[2];
   c->min_planes = *std::min_element(planes.begin(), planes.end());
   c->registered = true;
-  if (!dense) {  // pose-major lists for the observation pass (sparse problems are small: built on the host)
-    std::vector<int64_t> row_ptr(M + 1);
-    std::vector<int32_t> pidx(c->K);
-    CUDA_TRY(cudaMemcpy(row_ptr.data(), c->row_ptr, sizeof(int64_t) * (M + 1), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(pidx.data(), c->pose_idx, sizeof(int32_t) * c->K, cudaMemcpyDeviceToHost));
-    std::vector<int> ptr(N + 1, 0), cobs(c->K), cvox(c->K);
-    for (int i = 0; i < N; i++) ptr[i + 1] = ptr[i] + planes[i];
-    std::vector<int> cur(ptr.begin(), ptr.end() - 1);
-    for (int64_t v = 0; v < M; v++)
-      for (int64_t s = row_ptr[v]; s < row_ptr[v + 1]; s++) {
-        const int p = pidx[s];
-        cobs[cur[p]] = (int)s;
-        cvox[cur[p]] = (int)v;
-        cur[p]++;
-      }
-    c->csc_max_len = *std::max_element(planes.begin(), planes.end());
-    TRY(dev_alloc(&c->csc_ptr, (size_t)N + 1));
-    TRY(dev_alloc(&c->csc_obs, (size_t)c->K));
-    TRY(dev_alloc(&c->csc_vox, (size_t)c->K));
-    CUDA_TRY(cudaMemcpyAsync(c->csc_ptr, ptr.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->csc_obs, cobs.data(), sizeof(int) * c->K, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->csc_vox, cvox.data(), sizeof(int) * c->K, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-  }
+  if (!dense) TRY(build_pose_major_lists(c, planes.data()));  // pose-major lists for the observation sweep (device-built)
   return alloc_workspaces(c);
 }
 
@@ -512,15 +483,10 @@ extern "C" int balm_synth_virtual(balm_ctx *c, int64_t M, int64_t first_voxel, i
 }
 
 // ---------------- evaluation ----------------
-// Multi-GPU reduction of [H | g | r]: H is symmetric, so only its lower triangle travels. pack: column c of the lower
-// triangle (n - c entries, contiguous in H) -> offset c*n - c(c-1)/2 of the send buffer, followed by g and r;
-// unpack: the reduced triangle back into H, mirrored, plus g and r. 36 MB instead of 72 MB at N = 500.
-__global__ void pack_lower_kernel(const double *H, double *pack, int n) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
-  const size_t tri = (size_t)n * (n + 1) / 2;
-  if (r < n && r >= c) pack[(size_t)c * n - (size_t)c * (c - 1) / 2 + (r - c)] = H[(size_t)c * n + r];
-  if (c == 0 && r <= n) pack[tri + r] = H[(size_t)n * n + r];  // g (n entries) and r (1 entry) follow H in the ctx buffer
-}
+// Multi-GPU reduction of [H | g | r]: H is symmetric, so only its lower triangle travels. With a communicator attached the
+// assembly kernel writes column c of the lower triangle (n - c entries) at offset c*n - c(c-1)/2 of the send buffer,
+// followed by g and r, INSTEAD of the full matrix; after the all-reduce unpack_lower_kernel writes H (both halves), g and
+// r. 36 MB instead of 72 MB on the wire at N = 500, and no extra pass over the matrix.
 __global__ void unpack_lower_kernel(const double *pack, double *H, int n) {
   __shared__ double tile[32][33];
   const int bc = blockIdx.y, br = blockIdx.x;  // 32 x 32 block (block row br >= block column bc)
@@ -574,6 +540,7 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
   }
   for (int64_t v0 = head; v0 < end; v0 += c->VB) {
     const int64_t v1 = std::min(end, v0 + c->VB);
+    TRY(launch_csc_batch(c, v0, v1));  // sparse problems: every pose's list restricted to this batch's voxels
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     if (stats_cached) CUDA_TRY(cudaMemcpyAsync(r_dev, c->scal + BALM_SCAL_RCUR, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     else TRY(launch_voxel_stats(c, poses, v0, v1, c->stats, include_fix, r_dev));
@@ -604,14 +571,14 @@ static int evaluate_dev(balm_ctx *c, const double *poses, int64_t head, int64_t 
     TRY(launch_assemble(c));
     CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
   }
-  if (c->world > 1 && c->comm) {
+  if (c->world > 1 && c->comm) {  // the assembly wrote the lower triangle | g into c->Hpack (an empty range: zeros)
     const int n = c->n;
-    const size_t cnt = (size_t)n * (n + 1) / 2 + n + 1;
-    if (!c->Hpack) TRY(dev_alloc(&c->Hpack, cnt));
-    pack_lower_kernel<<<dim3((n + 256) / 256, n), 256, 0, c->stream>>>(c->H, c->Hpack, n);
+    const size_t tri = (size_t)n * (n + 1) / 2, cnt = tri + n + 1;
+    if (end > head) CUDA_TRY(cudaMemcpyAsync(c->Hpack + tri + n, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    else CUDA_TRY(cudaMemsetAsync(c->Hpack, 0, sizeof(double) * cnt, c->stream));
     TRY(allreduce_sum(c, c->Hpack, cnt));
     unpack_lower_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), dim3(32, 32), 0, c->stream>>>(c->Hpack, c->H, n);
-    c->launches += 2;
+    c->launches += 1;
   }
   CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->scal, r_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -843,6 +810,22 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
   return BALM_OK;
 }
 
+// ---------------- pose covariance (covariance.cu) ----------------
+int pose_covariance_dev(balm_ctx *c, const double *poses_dev, const double *ccov_host, double point_noise, bool include_fix,
+                        double *Rraw_host, double *Rcov_host);
+int balm_cov_evaluate_hessian(balm_ctx *c, const double *poses_dev, bool include_fix) {
+  return evaluate_dev(c, poses_dev, 0, c->M, include_fix);
+}
+extern "C" int balm_pose_covariance(balm_ctx *c, const double *poses12, const double *c_cov81, double point_noise,
+                                    int include_fix, double *Rcov_raw, double *Rcov) {
+  if (!c || !poses12 || (!Rcov_raw && !Rcov)) { balm_set_error("balm_pose_covariance: bad arguments"); return BALM_ERR_INVALID; }
+  if (!c->registered || c->M < 1) { balm_set_error("balm_pose_covariance: no voxels registered"); return BALM_ERR_INVALID; }
+  if (c->world > 1) { balm_set_error("balm_pose_covariance: single-GPU contexts only"); return BALM_ERR_UNSUPPORTED; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(c->poses, poses12, sizeof(double) * 12 * c->N, cudaMemcpyHostToDevice, c->stream));
+  return pose_covariance_dev(c, c->poses, c_cov81, point_noise, include_fix != 0, Rcov_raw, Rcov);
+}
+
 // ---------------- multi-GPU ----------------
 extern "C" int balm_comm_unique_id(void *out128) {
   if (!out128) return BALM_ERR_INVALID;
@@ -863,6 +846,7 @@ extern "C" int balm_comm_init(balm_ctx *c, int rank, int world, const void *uniq
   CUDA_TRY(cudaSetDevice(c->device));
   NcclDyn::uid_t id;
   memcpy(&id, unique_id128, 128);
+  if (!c->Hpack) TRY(dev_alloc(&c->Hpack, (size_t)c->n * (c->n + 1) / 2 + c->n + 1));
   const int rc = g_nccl.CommInitRank(&c->comm, world, id, rank);
   if (rc != 0) {
     balm_set_error(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));

@@ -230,6 +230,7 @@ struct ObsArgs {
   const int *skip;      // OBS_INT8: the speculative single sweep was accepted -> nothing to do
   // csc
   const int *csc_ptr, *csc_obs, *csc_vox;
+  const int *csc_lo, *csc_hi;  // [N] this batch's segment of every pose's list
 };
 
 // One lane = one pose; a warp covers 32 consecutive poses and walks a chunk of voxels, so the observation
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
     t0 = a.v0 + (long long)blockIdx.x * a.chunk;
     t1 = t0 + a.chunk < a.v1 ? t0 + a.chunk : a.v1;
   } else {
-    const int b = active ? a.csc_ptr[i] : 0, e = active ? a.csc_ptr[i + 1] : 0;
+    const int b = active ? a.csc_lo[i] : 0, e = active ? a.csc_hi[i] : 0;
     t0 = b + (long long)blockIdx.x * a.chunk;
     t1 = t0 + a.chunk < e ? t0 + a.chunk : e;
   }
@@ -539,6 +540,7 @@ static void obs_fill(balm_ctx *c, ObsArgs &a, const double *poses, int64_t v0, i
   a.obs = c->obs; a.Kp = c->Kp; a.row_ptr = c->row_ptr; a.poses = poses; a.stats = c->stats;
   a.v0 = v0; a.v1 = v1; a.N = c->N; a.Np = c->Np; a.ldg = c->ldg; a.G = c->G; a.part = c->obs_part;
   a.csc_ptr = c->csc_ptr; a.csc_obs = c->csc_obs; a.csc_vox = c->csc_vox;
+  a.csc_lo = c->csc_lo; a.csc_hi = c->csc_hi;
   a.colmax = c->colmax;
 }
 

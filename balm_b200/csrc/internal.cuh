@@ -53,6 +53,7 @@ struct balm_ctx {
   double *fix = nullptr;          // SoA [10][M] or null
   int *csc_ptr = nullptr, *csc_obs = nullptr, *csc_vox = nullptr;  // pose-major lists (sparse problems)
   int csc_max_len = 0;
+  int *csc_lo = nullptr, *csc_hi = nullptr;  // [N] segment of every pose's list inside the current voxel batch (null: whole list)
   int min_planes = 0;             // min over poses of #voxels observing it (precheck, bavoxel.hpp:1071-1085)
   int *planes = nullptr;          // [2][N] device: this rank's per-pose voxel counts | their all-reduced sum
   bool registered = false;        // a voxel set (possibly empty: a rank whose shard has no voxels) is registered
@@ -271,6 +272,8 @@ int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bo
 int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch);
 int launch_assemble(balm_ctx *c);
+int build_pose_major_lists(balm_ctx *c, const int *planes_host);
+int launch_csc_batch(balm_ctx *c, int64_t v0, int64_t v1);
 int launch_ldlt_solve(balm_ctx *c, double u);
 int refine_solution(balm_ctx *c, int *still_bad);
 int launch_pose_update(balm_ctx *c, const double *poses_in, const double *dx, double *poses_out);
@@ -280,6 +283,7 @@ int launch_synth(balm_ctx *c, int64_t n_voxels, int64_t first_voxel, int pts, do
 int factor_kernels_setup();
 int syrk_f64_setup();
 int ldlt_setup();
+int covariance_setup();
 int tensor_syrk_init(balm_ctx *c);
 void tensor_syrk_free(balm_ctx *c);
 int tensor_syrk_check(balm_ctx *c);

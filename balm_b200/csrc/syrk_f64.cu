@@ -45,6 +45,7 @@ struct SyrkArgs {
   int splits;
   double *part;     // [splits][tiles][TILE*TILE] row-major tiles
   int accumulate;   // add to existing partials (batches after the first)
+  int row_xor;      // A operand taken from row (k ^ row_xor): 0 = SYRK; 4 = the partner rows of covariance.cu (Q V^T + V Q^T)
 };
 
 __device__ __forceinline__ void tile_coords(int t, int nb, int &bi, int &bj) {
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(SYRK_THREADS, 1) syrk_f64_kernel(SyrkArgs a) {
         const int rr = e >> 6, cc = (e & 63) * 2;
         const int64_t kr = k0 + rr;
         if (kr < k_end) {
-          cp_async16(sA + rr * LDS + cc, gA + (size_t)kr * a.ldg + cc);
+          cp_async16(sA + rr * LDS + cc, gA + (size_t)(kr ^ a.row_xor) * a.ldg + cc);
           cp_async16(sB + rr * LDS + cc, gB + (size_t)kr * a.ldg + cc);
         } else {
           *reinterpret_cast<double2 *>(sA + rr * LDS + cc) = make_double2(0.0, 0.0);
@@ -155,6 +156,7 @@ struct AsmArgs {
   int exact_diag;       // take the diagonal of G'^T G' from the fp64 sums of squares (tensor path)
   double *H;            // n x n
   double *g;            // n
+  double *pack;         // multi-GPU: write the lower triangle | g straight into the all-reduce buffer instead of H (or null)
 };
 
 // H(i,j) = -sum_splits S(i,j) (+ D block on the diagonal); lower triangle mirrored from the upper tiles.
@@ -183,7 +185,13 @@ __global__ void __launch_bounds__(1024) assemble_kernel(AsmArgs a) {
       const int q = 6 + r6 * 6 - r6 * (r6 - 1) / 2 + (c6 - r6);
       h += a.accum[(size_t)q * a.Np + pi];
     }
-    a.H[(size_t)r * a.n + c] = h;  // element (row c, col r): the mirrored (lower) one, coalesced in c
+    // element (row c, col r): the mirrored (lower) one, coalesced in c -- into H, or into column r of the packed triangle
+    if (a.pack) { if (c >= r) a.pack[(size_t)r * a.n - (size_t)r * (r - 1) / 2 + (c - r)] = h; }
+    else a.H[(size_t)r * a.n + c] = h;
+  }
+  if (a.pack) {
+    if (bx == 0 && ty == 0 && c < a.n) a.pack[(size_t)a.n * (a.n + 1) / 2 + c] = a.accum[(size_t)(c % 6) * a.Np + c / 6];
+    return;
   }
   tile[ty][tx] = h;
   __syncthreads();
@@ -196,8 +204,11 @@ __global__ void __launch_bounds__(1024) assemble_kernel(AsmArgs a) {
 
 }  // namespace
 
-int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch) {
-  SyrkArgs a{c->G, rows, c->ldg, c->syrk_nb, c->syrk_tiles, c->syrk_splits, c->syrk_part, first_batch ? 0 : 1};
+int launch_syrk_f64_on(balm_ctx *c, const double *G, int64_t rows, bool first_batch, int row_xor);
+int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch) { return launch_syrk_f64_on(c, c->G, rows, first_batch, 0); }
+
+int launch_syrk_f64_on(balm_ctx *c, const double *G, int64_t rows, bool first_batch, int row_xor) {
+  SyrkArgs a{G, rows, c->ldg, c->syrk_nb, c->syrk_tiles, c->syrk_splits, c->syrk_part, first_batch ? 0 : 1, row_xor};
   const int smem = 2 * STAGE_DOUBLES * (int)sizeof(double);
   const int items = a.tiles * a.splits;
   const int grid = items < c->sm_count ? items : c->sm_count;
@@ -209,7 +220,7 @@ int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch) {
 
 int launch_assemble(balm_ctx *c) {
   AsmArgs a{c->syrk_part, c->syrk_splits, c->syrk_tiles, c->syrk_nb, c->accum, c->N, c->Np, c->n,
-            c->prec == BALM_PREC_TENSOR ? 1 : 0, c->H, c->g};
+            c->prec == BALM_PREC_TENSOR ? 1 : 0, c->H, c->g, (c->world > 1 && c->comm) ? c->Hpack : nullptr};
   const int nbb = (c->n + 31) / 32;
   dim3 block(32, 32), grid(nbb, nbb);
   assemble_kernel<<<grid, block, 0, c->stream>>>(a);

@@ -134,6 +134,19 @@ void balm_default_assoc_opts(balm_assoc_opts *opts);
 int balm_cut_voxels(balm_ctx *ctx, int64_t n_points, const float *xyz, const int32_t *frame, const double *poses12,
                     const balm_assoc_opts *opts, int64_t *n_voxels_out, int64_t *n_obs_out);
 
+/* Pose-covariance propagation of the consistency experiment:
+ *   Rcov_raw = sum over observations of  Ls c_cov Ls^T      -- VOX_HESS::left_jacobian_point + BALM2::multi_second
+ *                                                              (src/simulation/BAs_left.hpp:342-473, 995-1023)
+ *   Rcov     = H^-1 Rcov_raw H^-T                            -- the tail of BALM2::damping_iter (BAs_left.hpp:1089-1096)
+ * at the poses given (normally the output of balm_damping_iter). c_cov81: K x 81 doubles, the 9 x 9 covariance of every
+ * cluster's parameters (P00,P01,P02,P11,P12,P22,v0,v1,v2) in the order of obs10, i.e. PointCluster::c_cov
+ * (src/simulation/toolss.hpp:288,341); NULL derives it from the cluster moments for isotropic point noise of standard
+ * deviation point_noise, which is exactly what PointCluster::push accumulates (toolss.hpp:311-343). include_fix: the fix
+ * clusters take part in the voxel statistics and in H (BAs_left.hpp:183-185); without them H is singular (gauge) and the
+ * call fails with BALM_ERR_NOT_PD when Rcov is requested. Either output (n x n, column-major, symmetric) may be NULL. */
+int balm_pose_covariance(balm_ctx *ctx, const double *poses12, const double *c_cov81, double point_noise, int include_fix,
+                         double *Rcov_raw, double *Rcov);
+
 /* Multi-GPU: voxels are sharded across ranks by the caller (each rank registers its own shard); the library
  * all-reduces [H | g | r] with NCCL after every evaluation and the scalar after every residual pass.
  * unique_id: 128 bytes from balm_comm_unique_id() on rank 0, broadcast by the caller (torch.distributed, MPI). */

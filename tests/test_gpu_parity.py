@@ -175,8 +175,9 @@ def test_voxel_range_semantics():
 
 
 @pytest.mark.parametrize("prec", PRECS)
-def test_batched_evaluation_equals_single_batch(monkeypatch, prec):
-    sc = scenes.make_scene(n_poses=16, n_planes=300, seed=23)
+@pytest.mark.parametrize("drop", [0.0, 0.4])   # 0.4: sparse co-visibility in several voxel batches (pose-major lists cut per batch)
+def test_batched_evaluation_equals_single_batch(monkeypatch, prec, drop):
+    sc = scenes.make_scene(n_poses=16, n_planes=300, seed=23, drop=drop)
     c1 = _ctx(sc, prec)
     H1, g1, r1 = c1.evaluate(sc["poses_init"])
     monkeypatch.setenv("BALM_G_BUDGET_MB", "1")  # 1 MiB of G' -> many voxel batches
