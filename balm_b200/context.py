@@ -118,6 +118,19 @@ class Context:
                    recomputed_hess=bool(t.recomputed_hess), not_pd=bool(t.not_pd)) for t in trace[:n_it.value]]
         return poses, tr, (per_iter[:n_it.value] if want_per_iter else None)
 
+    def marginalize(self, mg_size, poses12, min_ps=15):
+        """OCTO_TREE_ROOT::marginalize on the registered voxel set (bavoxel.hpp:948-963, 778-816) -> (n_voxels, n_obs)."""
+        poses12 = np.ascontiguousarray(poses12, dtype=np.float64)
+        M, K = C.c_int64(), C.c_int64()
+        L.check(L.lib().balm_marginalize(self._h, int(mg_size), _p(poses12), int(min_ps), C.byref(M), C.byref(K)))
+        self.M = M.value
+        return M.value, K.value
+
+    def download_fix(self):
+        fix = np.zeros((self.M, 10))
+        L.check(L.lib().balm_download_fix(self._h, _p(fix)))
+        return fix
+
     def pose_covariance(self, poses12, point_noise=0.0, c_cov=None, include_fix=False, want_raw=True, want_cov=True):
         """left_jacobian_point / multi_second / H^-1 Rcov H^-T (BAs_left.hpp:342-473, 995-1023, 1089-1096).
         -> (Rcov_raw, Rcov); c_cov: K x 9 x 9 per-observation cluster covariances, or None for isotropic point noise."""

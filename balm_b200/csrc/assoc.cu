@@ -475,3 +475,105 @@ int launch_csc_batch(balm_ctx *c, int64_t v0, int64_t v1) {
   CUDA_TRY(cudaGetLastError());
   return BALM_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sliding-window marginalisation on the registered voxel set:
+//   OCTO_TREE_NODE::to_margi (bavoxel.hpp:778-816) on every plane leaf -- the clusters of the oldest mg_size scans,
+//   transformed by their (optimised) poses, are folded into the leaf's fix_point when fix_point.N < 50 (:790-795), the
+//   remaining scans shift down by mg_size (:797-803) -- followed by what tras_opt / push_voxel keep of the leaf
+//   (bavoxel.hpp:908-929: fewer than min_ps points left -> not pushed; :32-37: fewer than 2 observing scans -> not pushed;
+//   coe = number of points left, :42-44).
+// The flattened voxel set has no octree any more, so a leaf that is not pushed is dropped together with its fix cluster
+// (in the reference it stays in the map for later scans); documented in DESIGN.md.
+namespace {
+__global__ void marg_count_kernel(const long long *row_ptr, const int *pose_idx, const double *obs, int64_t Kp, int64_t M,
+                                  int mg, int min_ps, int *keep, int *cnt) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= M) return;
+  int k = 0;
+  double pts = 0.0;
+  for (long long s = row_ptr[v]; s < row_ptr[v + 1]; s++)
+    if (pose_idx[s] >= mg) { k++; pts += obs[9 * Kp + s]; }
+  const int kp = ((int)pts >= min_ps && k >= 2) ? 1 : 0;
+  keep[v] = kp;
+  cnt[v] = kp ? k : 0;
+}
+__global__ void marg_emit_kernel(const long long *row_ptr, const int *pose_idx, const double *obs, int64_t Kp,
+                                 const double *fix /*SoA [10][M] or null*/, int64_t M, const double *poses, int mg,
+                                 const int *keep, const int *vscan, const int *oscan, long long *row_ptr_out,
+                                 int *pose_idx_out, double *obs10_out, double *fix10_out, double *coe_out, int64_t Mout,
+                                 int64_t Kout) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v == 0) row_ptr_out[Mout] = Kout;
+  if (v >= M || !keep[v]) return;
+  const int nv = vscan[v];
+  long long o = oscan[v];
+  row_ptr_out[nv] = o;
+  double f[10];
+  for (int c = 0; c < 10; c++) f[c] = fix ? fix[c * M + v] : 0.0;
+  const bool absorb = (int)f[9] < 50;  // fix_point.N < 50 (bavoxel.hpp:790; push_state == 1 for a registered plane leaf)
+  double pts = 0.0;
+  for (long long s = row_ptr[v]; s < row_ptr[v + 1]; s++) {
+    double ob[10];
+    for (int c = 0; c < 10; c++) ob[c] = obs[c * Kp + s];
+    const int p = pose_idx[s];
+    if (p < mg) {
+      if (absorb) {  // fix_point += sig_tran[i]  (transform: tools.hpp:333-339)
+        double r[9], t[3];
+        load_pose(poses + 12 * p, r, t);
+        const WC w = world_cluster(ob, r, t);
+        f[0] += w.p00; f[1] += w.p01; f[2] += w.p02; f[3] += w.p11; f[4] += w.p12; f[5] += w.p22;
+        f[6] += w.v0; f[7] += w.v1; f[8] += w.v2; f[9] += w.n;
+      }
+    } else {
+      for (int c = 0; c < 10; c++) obs10_out[o * 10 + c] = ob[c];
+      pose_idx_out[o] = p - mg;
+      pts += ob[9];
+      o++;
+    }
+  }
+  for (int c = 0; c < 10; c++) fix10_out[(size_t)nv * 10 + c] = f[c];
+  coe_out[nv] = pts;
+}
+}  // namespace
+
+int marginalize_build(balm_ctx *c, int mg, const double *poses_dev, int min_ps, int64_t *M_out, int64_t *K_out,
+                      int (*reg)(balm_ctx *, int64_t, const int64_t *, const int32_t *, const double *, const double *,
+                                 const double *, int64_t)) {
+  const int64_t M = c->M;
+  cudaStream_t st = c->stream;
+  ScratchPool pool;
+  int *keep = nullptr, *cnt = nullptr, *vscan = nullptr, *oscan = nullptr;
+  ATRY(pool.get(&keep, (size_t)M)); ATRY(pool.get(&cnt, (size_t)M)); ATRY(pool.get(&vscan, (size_t)M)); ATRY(pool.get(&oscan, (size_t)M));
+  const unsigned gb = (unsigned)((M + 127) / 128);
+  marg_count_kernel<<<gb, 128, 0, st>>>(c->row_ptr, c->pose_idx, c->obs, c->Kp, M, mg, min_ps, keep, cnt);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, keep, vscan, (int)M, st);
+  char *tmp = nullptr;
+  ATRY(pool.get(&tmp, tb));
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tb, keep, vscan, (int)M, st));
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, oscan, (int)M, st));
+  int last[4] = {0, 0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(&last[0], keep + M - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&last[1], vscan + M - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&last[2], cnt + M - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&last[3], oscan + M - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const int64_t Mout = (int64_t)last[0] + last[1], Kout = (int64_t)last[2] + last[3];
+  *M_out = Mout;
+  *K_out = Kout;
+  long long *rp = nullptr;
+  int *pi = nullptr;
+  double *ob = nullptr, *fx = nullptr, *co = nullptr;
+  ATRY(pool.get(&rp, (size_t)Mout + 1)); ATRY(pool.get(&pi, (size_t)Kout)); ATRY(pool.get(&ob, (size_t)Kout * 10));
+  ATRY(pool.get(&fx, (size_t)Mout * 10)); ATRY(pool.get(&co, (size_t)Mout));
+  marg_emit_kernel<<<gb, 128, 0, st>>>(c->row_ptr, c->pose_idx, c->obs, c->Kp, c->fix, M, poses_dev, mg, keep, vscan, oscan, rp,
+                                       pi, ob, fx, co, Mout, Kout);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 4;
+  if (Mout < 1) { balm_set_error("balm_marginalize: no voxel is left with two observing scans"); return BALM_ERR_INVALID; }
+  // re-register from the device arrays (copies them, transposes the observations, rebuilds the pose-major lists)
+  return reg(c, Mout, (const int64_t *)rp, pi, ob, fx, co, Kout);
+}

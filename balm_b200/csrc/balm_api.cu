@@ -810,6 +810,32 @@ extern "C" int balm_damping_iter(balm_ctx *c, double *poses12, const balm_lm_opt
   return BALM_OK;
 }
 
+// ---------------- sliding-window marginalisation (assoc.cu) ----------------
+int marginalize_build(balm_ctx *c, int mg, const double *poses_dev, int min_ps, int64_t *M_out, int64_t *K_out,
+                      int (*reg)(balm_ctx *, int64_t, const int64_t *, const int32_t *, const double *, const double *,
+                                 const double *, int64_t));
+extern "C" int balm_marginalize(balm_ctx *c, int mg_size, const double *poses12, int min_ps, int64_t *n_voxels_out,
+                                int64_t *n_obs_out) {
+  if (!c || !poses12 || mg_size < 1 || mg_size >= c->N) { balm_set_error("balm_marginalize: bad arguments"); return BALM_ERR_INVALID; }
+  if (!c->registered || c->M < 1) { balm_set_error("balm_marginalize: no voxels registered"); return BALM_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(c->poses, poses12, sizeof(double) * 12 * c->N, cudaMemcpyHostToDevice, c->stream));
+  int64_t M = 0, K = 0;
+  TRY(marginalize_build(c, mg_size, c->poses, min_ps, &M, &K, balm_set_voxels_dev));
+  if (n_voxels_out) *n_voxels_out = M;
+  if (n_obs_out) *n_obs_out = K;
+  return BALM_OK;
+}
+extern "C" int balm_download_fix(balm_ctx *c, double *fix10) {
+  if (!c || !fix10 || !c->registered) { balm_set_error("balm_download_fix: bad arguments"); return BALM_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  std::vector<double> soa((size_t)10 * c->M, 0.0);
+  if (c->fix) CUDA_TRY(cudaMemcpy(soa.data(), c->fix, sizeof(double) * 10 * c->M, cudaMemcpyDeviceToHost));
+  for (int64_t v = 0; v < c->M; v++)
+    for (int q = 0; q < 10; q++) fix10[v * 10 + q] = soa[(size_t)q * c->M + v];
+  return BALM_OK;
+}
+
 // ---------------- pose covariance (covariance.cu) ----------------
 int pose_covariance_dev(balm_ctx *c, const double *poses_dev, const double *ccov_host, double point_noise, bool include_fix,
                         double *Rraw_host, double *Rcov_host);

@@ -134,6 +134,19 @@ void balm_default_assoc_opts(balm_assoc_opts *opts);
 int balm_cut_voxels(balm_ctx *ctx, int64_t n_points, const float *xyz, const int32_t *frame, const double *poses12,
                     const balm_assoc_opts *opts, int64_t *n_voxels_out, int64_t *n_obs_out);
 
+/* Sliding-window marginalisation of the registered voxel set =
+ * OCTO_TREE_ROOT::marginalize -> OCTO_TREE_NODE::to_margi on every plane leaf (bavoxel.hpp:948-963, 778-816) followed by
+ * the re-registration tras_opt -> push_voxel would make (bavoxel.hpp:908-929, 30-51): the clusters of the oldest mg_size
+ * scans, transformed by poses12 (the optimised poses, N x 12), are added to the voxel's fix cluster when that holds fewer
+ * than 50 points (:790), the remaining scans shift down by mg_size (pose slot i := old slot i + mg_size; the caller shifts
+ * its pose array the same way, consistency.cpp:137-140), voxels left with fewer than min_ps points or fewer than two
+ * observing scans are not pushed, coe = points left. Everything stays in HBM; the context is re-registered as if
+ * balm_set_voxels had been called with the new set (n_poses unchanged: the last mg_size slots are empty until new scans
+ * are associated). balm_download_fix copies the fix clusters (M x 10) back. */
+int balm_marginalize(balm_ctx *ctx, int mg_size, const double *poses12, int min_ps, int64_t *n_voxels_out,
+                     int64_t *n_obs_out);
+int balm_download_fix(balm_ctx *ctx, double *fix10);
+
 /* Pose-covariance propagation of the consistency experiment:
  *   Rcov_raw = sum over observations of  Ls c_cov Ls^T      -- VOX_HESS::left_jacobian_point + BALM2::multi_second
  *                                                              (src/simulation/BAs_left.hpp:342-473, 995-1023)

@@ -122,3 +122,42 @@ def synthetic_scans(n_poses=12, pts_per_scan=6000, seed=5, room=6.0):
     noisy = [(Rs[i] @ scenes.exp_so3(rng.normal(0, 0.003, 3)), ps[i] + rng.normal(0, 0.01, 3)) for i in range(n_poses)]
     noisy[0] = (Rs[0], ps[0])
     return np.concatenate(pts), np.concatenate(frs), noisy
+
+
+def marginalize_ref(n_poses, row_ptr, pose_idx, obs10, fix10, poses12, mg_size, min_ps=15):
+    """numpy restatement of the sliding-window step on a flattened set of plane leaves:
+      OCTO_TREE_NODE::to_margi   bavoxel.hpp:778-816  (sig_tran = transform(sig_orig, x_poses); fix_point += the oldest
+                                                       mg_size clusters if fix_point.N < 50 and push_state == 1; shift)
+      OCTO_TREE_NODE::tras_opt   bavoxel.hpp:908-929  (fewer than min_ps points left -> not pushed)
+      VOX_HESS::push_voxel       bavoxel.hpp:30-51    (fewer than 2 observing scans -> not pushed; coe = points left)
+    -> row_ptr, pose_idx, obs10, fix10, coe of the voxels that are pushed again, in the original order."""
+    rp, pi, ob, fx, co = [0], [], [], [], []
+    for a in range(len(row_ptr) - 1):
+        fix = np.zeros(10) if fix10 is None else np.array(fix10[a], dtype=np.float64)
+        absorb = int(fix[9]) < 50
+        keep = []
+        for s in range(row_ptr[a], row_ptr[a + 1]):
+            i = pose_idx[s]
+            if i < mg_size:
+                if absorb:
+                    o = obs10[s]
+                    R = poses12[i][:9].reshape(3, 3).T
+                    p = poses12[i][9:12]
+                    P = np.array([[o[0], o[1], o[2]], [o[1], o[3], o[4]], [o[2], o[4], o[5]]])
+                    v, n = o[6:9], o[9]
+                    Rv = R @ v                                                   # PointCluster::transform, tools.hpp:333-339
+                    Pw = R @ P @ R.T + np.outer(Rv, p) + np.outer(p, Rv) + n * np.outer(p, p)
+                    fix += np.array([Pw[0, 0], Pw[0, 1], Pw[0, 2], Pw[1, 1], Pw[1, 2], Pw[2, 2], *(Rv + n * p), n])
+            else:
+                keep.append(s)
+        pts = sum(obs10[s][9] for s in keep)
+        if int(pts) < min_ps or len(keep) < 2:
+            continue
+        for s in keep:
+            ob.append(obs10[s])
+            pi.append(pose_idx[s] - mg_size)
+        rp.append(len(pi))
+        fx.append(fix)
+        co.append(float(pts))
+    return (np.array(rp, dtype=np.int64), np.array(pi, dtype=np.int32), np.array(ob).reshape(-1, 10),
+            np.array(fx).reshape(-1, 10), np.array(co))
