@@ -44,89 +44,125 @@ __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// The 64x64 diagonal block is factored in four 16-column sub-panels. A sub-panel is factored by TWO warps (one
-// thread per row, its 16 panel entries in registers) with a 64-thread named barrier per column -- the serial chain
-// of the whole solve is n = 6N of these column steps, so each step is kept to: post column -> barrier -> reciprocal
-// -> <=15 FMAs. The rank-16 trailing update and the assembly of X = L11^-1 from 16x16 inverses use all 256 threads.
+// The 64x64 diagonal block is factored in four 16-column sub-panels. The serial chain of the whole solve is n = 6N column
+// steps, so the 16 x 16 diagonal block of a sub-panel is factored by ONE warp with its rows in registers and the columns
+// exchanged by shuffles (no shared-memory round trip, no barrier per column), which also yields its inverse; the rows
+// below follow as a 16-wide GEMM with that inverse, the rank-16 trailing update and the assembly of X = L11^-1 from the
+// 16x16 inverses use all 256 threads. (Round 1 factored the whole 64-row sub-panel column by column on two warps with a
+// named barrier per column: 21 us per 64 x 64 block against 12 us now.)
 // In: S = the block (lower triangle), Xs = 0, all threads synchronised. Out: S = L (below the diagonal) and d (on
 // it), Xs = L11^-1 (lower), all threads synchronised. Returns true if a pivot was zero / non-finite.
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+  return t;
+}
+// 1/d to full double precision off the slow division path: hardware seed (rcp.approx.ftz.f64, ~2^-23) + two Newton steps.
+// The reciprocal of the pivot is on the serial chain of every column, the IEEE division costs three times as much.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  return fma(x, e, x);
+}
 __device__ __forceinline__ bool diag_factor(double (*S)[NB + 1], double (*Xs)[NB + 1], double (*Wp)[17],
-                                            double (*col16)[16]) {
+                                            double (*col16)[16], unsigned long long *stamp = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   bool bad = false;
+  double *dinv16 = &col16[0][0];  // [16] reciprocals of the current sub-panel's pivots
 #pragma unroll 1
   for (int cb = 0; cb < NB; cb += 16) {
-    if (tid < NB) {  // ---- sub-panel factorisation: rows r >= cb, columns cb .. cb+15 ----
-      const int r = tid;
+    // ---- (1) the 16 x 16 diagonal block: ONE warp, rows in registers, columns exchanged by shuffles (no barrier on the
+    //      serial chain: per column one broadcast of the pivot, one shuffle per remaining column, one FMA each), then its
+    //      inverse X11 = L11^-1 by forward substitution on the identity, again shuffles only ----
+    if (warp == 0) {
+      const int i = lane & 15;  // lanes 16..31 mirror lanes 0..15
       double a[16];
 #pragma unroll
-      for (int k = 0; k < 16; k++) a[k] = S[r][cb + k];
+      for (int q = 0; q < 16; q++) a[q] = S[cb + i][cb + q];  // (entries above the diagonal are zero on entry and never used)
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        const int jc = cb + j;
-        if (r >= cb && r < cb + 16) col16[j & 1][r - cb] = a[j];  // unscaled column j at the panel's own rows
-        bar_sync_named(1, NB);
-        const double d = col16[j & 1][j];
+        const double d = __shfl_sync(0xffffffffu, a[j], j, 16);
         if (!(fabs(d) > 1e-290 && fabs(d) < 1e300)) bad = true;
-        const double dinv = __drcp_rn(d);
-        if (r > jc) {
-          const double l = a[j] * dinv;
+        const double dinv = fast_rcp(d);
+        const double aj = a[j];
 #pragma unroll
-          for (int k = j + 1; k < 16; k++) a[k] -= l * col16[j & 1][k];
-          a[j] = l;
+        for (int q = j + 1; q < 16; q++) {
+          const double cq = __shfl_sync(0xffffffffu, aj, q, 16);  // A[q][j] before scaling
+          a[q] = fma(-(aj * cq), dinv, a[q]);  // the product does not wait for the reciprocal; unmasked: what lands
+        }                                      // above the diagonal is never read
+        a[j] = (i > j) ? aj * dinv : aj;
+        if (i == j) dinv16[j] = dinv;
+      }
+      double xr[16];
+#pragma unroll
+      for (int q = 0; q < 16; q++) xr[q] = (q == i) ? 1.0 : 0.0;
+#pragma unroll
+      for (int j = 0; j < 15; j++) {
+        const double l = (i > j) ? a[j] : 0.0;
+#pragma unroll
+        for (int q = 0; q <= j; q++) {  // row j of the inverse is final and has entries q <= j only
+          const double xj = __shfl_sync(0xffffffffu, xr[q], j, 16);
+          xr[q] -= l * xj;
         }
       }
-      if (r >= cb) {
+      if (lane < 16) {
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-          if (r >= cb + k) S[r][cb + k] = a[k];        // L (r > cb+k) and d (r == cb+k)
+        for (int q = 0; q < 16; q++) {
+          if (q <= i) S[cb + i][cb + q] = a[q];  // L (q < i) and d (q == i)
+          Xs[cb + i][cb + q] = xr[q];
         }
       }
     }
     __syncthreads();
-    if (tid < NB) {  // W = L_panel * d for the trailing update
-      const int r = tid;
+    // ---- (2) the rows below: W = A21 X11^T (a 16-wide GEMM instead of a sequential triangular solve), L21 = W d^-1 ----
+    {
+      const int nrow = NB - cb - 16;
+      double wv[3];
 #pragma unroll
-      for (int k = 0; k < 16; k++) Wp[r][k] = (r > cb + k) ? S[r][cb + k] * S[cb + k][cb + k] : 0.0;
+      for (int t = 0; t < 3; t++) {
+        const int e = tid + t * 256;
+        wv[t] = 0.0;
+        if (e < nrow * 16) {
+          const int r = cb + 16 + (e >> 4), q = e & 15;
+          double sacc = 0.0;
+#pragma unroll
+          for (int m = 0; m < 16; m++) sacc += (m <= q) ? S[r][cb + m] * Xs[cb + q][cb + m] : 0.0;
+          wv[t] = sacc;
+        }
+      }
+      __syncthreads();  // every thread has read the unscaled panel entries it needs
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        const int e = tid + t * 256;
+        if (e < nrow * 16) {
+          const int r = cb + 16 + (e >> 4), q = e & 15;
+          Wp[r][q] = wv[t];
+          S[r][cb + q] = wv[t] * dinv16[q];
+        }
+      }
     }
     __syncthreads();
-    {  // trailing block in 16x16 sub-blocks: thread (ri, ci) owns one element of each lower sub-block
+    {  // ---- (3) trailing block in 16x16 sub-blocks: thread (ri, ci) owns one element of each lower sub-block ----
       const int ri = tid >> 4, ci = tid & 15;
       for (int rb2 = cb + 16; rb2 < NB; rb2 += 16)
         for (int cb2 = cb + 16; cb2 <= rb2; cb2 += 16) {
           const int r = rb2 + ri, c = cb2 + ci;
           if (r >= c) {
-            double s = 0.0;
+            double sacc = 0.0;
 #pragma unroll
-            for (int k = 0; k < 16; k++) s += Wp[r][k] * S[c][cb + k];
-            S[r][c] -= s;
+            for (int q = 0; q < 16; q++) sacc += Wp[r][q] * S[c][cb + q];
+            S[r][c] -= sacc;
           }
         }
     }
     __syncthreads();
+    if (stamp && tid == 0) stamp[1 + (cb >> 4)] = gtime_ns();
   }
+  bad = __syncthreads_or(bad ? 1 : 0) != 0;
 
-  // ---- X = L11^-1: 16x16 diagonal-block inverses (one warp each, shuffles only) ----
-  if (warp < 4) {
-    const int cb = 16 * warp, i = lane & 15;
-    double xr[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) xr[k] = (k == i) ? 1.0 : 0.0;
-#pragma unroll
-    for (int j = 0; j < 15; j++) {
-      const double l = (i > j) ? S[cb + i][cb + j] : 0.0;
-#pragma unroll
-      for (int k = 0; k <= j; k++) {  // row j of the inverse is final and has entries k <= j only
-        const double xj = __shfl_sync(0xffffffffu, xr[k], j, 16);
-        xr[k] -= l * xj;
-      }
-    }
-    if (lane < 16) {
-#pragma unroll
-      for (int k = 0; k < 16; k++) Xs[cb + i][cb + k] = xr[k];
-    }
-  }
-  __syncthreads();
   // ---- off-diagonal blocks by block rows: X_bc = -X_bb * sum_{m=c}^{b-1} L_bm X_mc ----
 #pragma unroll 1
   for (int b = 1; b < 4; b++) {
@@ -607,8 +643,21 @@ __device__ __forceinline__ void chain(const Args &a, double *smem) {
       // mini-panel of step k-1 for row block k: L_{k,k-1}, W_{k,k-1}; mini-update of A_kk and of b_k
       if (tid == 0) wait_ge(a.upd + k * nt + (k - 1), k - 1);
       if (tid == 32) wait_ge(a.rhs_cnt + k, k - 1);
+      if (tid == 64) wait_ge(a.upd + k * nt + k, k - 1);  // the diagonal block has every update but the chain's own
       if (a.trace && tid == 0) a.trace[4 * k + 1] = gtime();
       __syncthreads();
+    }
+    // the diagonal block is requested now (lower triangle; rows/cols of a short last block act as identity): its L2
+    // round trip overlaps the mini-panel
+    double sld[16];
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+      const int e = tid + it * 256, r = e & (NB - 1), c = e >> 6;
+      double v = (r == c) ? 1.0 : 0.0;
+      if (r < nbw && c < nbw && r >= c) v = ld_cg(a.A + (size_t)(j0 + c) * n + j0 + r);
+      sld[it] = v;
+    }
+    if (k > 0) {
       if (tid >= T && tid < 2 * T) vec[tid] = ld_cg(a.ysol + (k - 1) * T + tid - T);
       panel_tile(a, k, k - 1, t0, t1, /*sL=*/t2, /*sW=*/t3, vec);
 #pragma unroll 4
@@ -625,19 +674,15 @@ __device__ __forceinline__ void chain(const Args &a, double *smem) {
       tile_mma(accu, t2, t3, nullptr);  // L W^T
       __syncthreads();
       if (tid == 0) { __threadfence(); st_release(a.pdone + k * nt + (k - 1), 1); }
-      if (tid == 0) wait_ge(a.upd + k * nt + k, k - 1);
       if (a.trace && tid == 0) a.trace[4 * k + 2] = gtime();
-      __syncthreads();
     } else if (tid < T) {
       bloc = (tid < nbw) ? a.sol[j0 + tid] : 0.0;
     }
-    // the diagonal block (lower triangle; rows/cols of a short last block act as identity), minus the mini-update
+    // the diagonal block into shared memory, minus the mini-update
 #pragma unroll
     for (int it = 0; it < 16; it++) {
       const int e = tid + it * 256, r = e & (NB - 1), c = e >> 6;
-      double v = (r == c) ? 1.0 : 0.0;
-      if (r < nbw && c < nbw && r >= c) v = ld_cg(a.A + (size_t)(j0 + c) * n + j0 + r);
-      S[r][c] = v;
+      S[r][c] = sld[it];
       Xs[r][c] = 0.0;
     }
     if (tid < NB) bvec[tid] = bloc;
@@ -654,7 +699,10 @@ __device__ __forceinline__ void chain(const Args &a, double *smem) {
           }
       __syncthreads();
     }
-    const bool bad = diag_factor(S, Xs, Wp, col16);
+    unsigned long long *stamp = (a.trace && k == 20) ? a.trace + 4 * nt : nullptr;  // fine timeline of one step
+    if (stamp && tid == 0) stamp[0] = gtime();
+    const bool bad = diag_factor(S, Xs, Wp, col16, stamp);
+    if (stamp && tid == 0) stamp[5] = gtime();
     if (bad && tid == 0) atomicOr(&a.flags[0], 1);
     double *Xcm = a.Xinv + (size_t)k * NB * NB;
 #pragma unroll 4
@@ -670,6 +718,7 @@ __device__ __forceinline__ void chain(const Args &a, double *smem) {
       if (tid < nbw) a.ysol[j0 + tid] = sacc;
     }
     __syncthreads();
+    if (stamp && tid == 0) stamp[6] = gtime();
     if (tid == 0) { __threadfence(); st_release(a.xdone + k, 1); }
     if (a.trace && tid == 0) a.trace[4 * k + 3] = gtime();
   }

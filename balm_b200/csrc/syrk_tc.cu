@@ -22,6 +22,7 @@
 //              fp64 partial tile to global (same partial layout as the fp64 path -> same assemble kernel)
 #include <cuda.h>
 #include <vector>
+#include <algorithm>
 #include "internal.cuh"
 
 namespace {
@@ -384,7 +385,8 @@ __device__ __forceinline__ void syrk_tc_body(const CUtensorMap &tmap, const CUte
       const bool empty_item = k_begin >= a.rows;
       if (!mbar_wait(tmem_full, n_done & 1, a.err)) break;
       tc_fence_after();
-      double *out = a.part + ((size_t)sp * a.tiles + t) * (TILE * TILE) + (size_t)row * TILE;
+      double *tile_out = a.part + ((size_t)sp * a.tiles + t) * (TILE * TILE);
+      double *out = tile_out + (size_t)row * TILE;
       const double isc_row = __ldg(a.isc + bi * TILE + row);
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
@@ -618,12 +620,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const int sp = item / a.n_pairs;
       const int bi = (pr.x >> (rank ? 16 : 0)) & 255, bj = (pr.x >> 8) & 255;
       const bool store = !((pr.y & 2) && rank == 1);
-      const int t = bi <= bj ? bi * a.nb - bi * (bi - 1) / 2 + (bj - bi) : 0;
+      const bool flipped = bi > bj;  // computed as (A = bi, B = bj) with bi > bj: the transpose of tile (bj, bi)
+      const int ti = flipped ? bj : bi, tj = flipped ? bi : bj;
+      const int t = ti * a.nb - ti * (ti - 1) / 2 + (tj - ti);
       const int64_t k_begin = (int64_t)sp * per;
       const bool empty_item = k_begin >= a.rows;
       if (!mbar_wait(tmem_full, n_done & 1, a.err)) break;
       tc_fence_after();
-      double *out = a.part + ((size_t)sp * a.tiles + t) * (TILE * TILE) + (size_t)row * TILE;
+      double *tile_out = a.part + ((size_t)sp * a.tiles + t) * (TILE * TILE);
+      double *out = tile_out + (size_t)row * TILE;
       const double isc_row = __ldg(a.isc + bi * TILE + row);
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
@@ -645,7 +650,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             for (int q = 0; q < 16; q++) val[q] = val[q] * inv256 + (double)v[q];
           }
         }
-        if (store) {
+        if (store && !flipped) {
 #pragma unroll
           for (int q = 0; q < 16; q += 2) {
             const double2 sc = *reinterpret_cast<const double2 *>(a.isc + bj * TILE + c0 + q);
@@ -656,6 +661,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
               w.x += old.x;
               w.y += old.y;
             }
+            *p = w;
+          }
+        } else if (store) {  // element (row, c0+q) of the computed product is element (c0+q, row) of the stored tile
+#pragma unroll
+          for (int q = 0; q < 16; q++) {
+            double w = val[q] * isc_row * __ldg(a.isc + bj * TILE + c0 + q);
+            double *p = tile_out + (size_t)(c0 + q) * TILE + row;
+            if (a.accumulate) w += *p;
             *p = w;
           }
         }
@@ -876,15 +889,30 @@ int tensor_syrk_init(balm_ctx *c) {
     CUDA_TRY(cudaMemcpy(st->pairs, pairs.data(), sizeof(int2) * pairs.size(), cudaMemcpyHostToDevice));
     const char *e = getenv("BALM_TC_PAIR");
     st->use_pairs = (e ? atoi(e) != 0 : false) && nb < 256 && (c->sm_count % 2 == 0);
-    // 2-SM list: rows (bi, bi+1) of block column bj; the lone diagonal tile of an even column is paired with the
-    // below-diagonal tile (bj+1, bj), whose result is discarded (flag 2)
+    // 2-SM list: every pair is two tiles that share their B block. Tile (bi, bj), bi <= bj, normally uses B = bj, so block
+    // column bj holds bj+1 tiles -- an odd number for even bj, which used to cost one wasted slot per even column (312
+    // slots for the 300 tiles of n = 3000). The product is symmetric, so a tile can just as well be computed in the other
+    // orientation (A = block bj, B = block bi: the transposed tile, stored transposed by the epilogue): for consecutive
+    // even columns j1 < j2 the tile (j1, j2) moves from column j2 to column j1, which makes both counts even. Only when the
+    // number of even columns is odd does one column keep a leftover, paired with a discarded duplicate (flag 2).
+    std::vector<std::vector<int>> rows_of(nb);  // A-block indices of the tiles computed with B = bj
+    for (int bj = 0; bj < nb; bj++)
+      for (int bi = 0; bi <= bj; bi++) rows_of[bj].push_back(bi);
+    if (!getenv("BALM_TC_NO_FLIP")) {
+      for (int j1 = 0; j1 + 2 < nb; j1 += 4) {
+        const int j2 = j1 + 2;
+        rows_of[j2].erase(std::find(rows_of[j2].begin(), rows_of[j2].end(), j1));  // tile (j1, j2) leaves column j2 ...
+        rows_of[j1].push_back(j2);                                                  // ... and joins column j1 as A = j2 > B = j1
+      }
+    }
     std::vector<int2> p2;
     for (int bj = 0; bj < nb; bj++) {
-      int bi = 0;
-      for (; bi + 1 <= bj; bi += 2) p2.push_back(make_int2(bi | (bj << 8) | ((bi + 1) << 16) | (bj << 24), 1));
-      if (bi <= bj) {
-        const int other = bi + 1 < nb ? bi + 1 : bi;  // last column: duplicate the tile itself
-        p2.push_back(make_int2(bi | (bj << 8) | (other << 16) | (bj << 24), 1 | 2));
+      const std::vector<int> &r = rows_of[bj];
+      size_t q = 0;
+      for (; q + 1 < r.size(); q += 2) p2.push_back(make_int2(r[q] | (bj << 8) | (r[q + 1] << 16) | (bj << 24), 1));
+      if (q < r.size()) {  // leftover: duplicate partner, result discarded
+        const int other = r[q] + 1 < nb ? r[q] + 1 : r[q];
+        p2.push_back(make_int2(r[q] | (bj << 8) | (other << 16) | (bj << 24), 1 | 2));
       }
     }
     st->n_pairs2 = (int)p2.size();

@@ -476,7 +476,9 @@ def main():
         planes = tm["digit_planes"]
         pairs = planes * (planes + 1) // 2
         nbk = (6 * N + 127) // 128
-        tiles_exec = sum(((bj + 2) // 2) * 2 for bj in range(nbk))  # 2-SM pairs: odd columns carry one redundant tile
+        # 2-SM pairs: every tile once (tiles of consecutive even block columns are flipped to make every column's count
+        # even); one duplicate slot only when the number of even columns is odd
+        tiles_exec = nbk * (nbk + 1) // 2 + (((nbk + 1) // 2) % 2)
         int8_ops = 2.0 * pairs * tiles_exec * 128 * 128 * 3 * M
         roof["digit_planes"] = planes
         roof["executed_int8_tops"] = int8_ops / (syrk_ms * 1e-3) / 1e12

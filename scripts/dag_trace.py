@@ -37,6 +37,11 @@ for k in range(nt):
     else:
         print(f"{k:4d} {(s - t0) / 1e3:8.1f} {(a - s) / 1e3:10.1f} {(b - a) / 1e3:12.1f} {(e - b) / 1e3:8.1f}")
 w = buf[4 * nt:].reshape(-1, 8).astype(np.int64)
+st = buf[4 * nt:4 * nt + 8].astype(np.int64)
+if nt > 20:
+    print("step 20 fine (us): mini-panel+load %.1f | sub-panels %s | X assembly %.1f | write-back %.1f | release %.1f" % (
+        (st[0] - ch[20, 0]) / 1e3, np.round(np.diff(st[0:5]) / 1e3, 1).tolist(), (st[5] - st[4]) / 1e3, (st[6] - st[5]) / 1e3,
+        (ch[20, 3] - st[6]) / 1e3))
 w = w[1:149]
 act = w[w[:, 2] > 0]
 print("workers: %d active, tasks/CTA min %d mean %.1f max %d; span mean %.1f us; us/task mean %.2f" % (
