@@ -21,11 +21,17 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <vector>
 #include "balm_b200.h"
 
 #ifdef BALM_B200_WITH_EIGEN
-// tools.hpp (PointCluster, IMUST, Eigen) must already be included by the translation unit.
+// tools.hpp (PointCluster, IMUST, Eigen, PCL's PointType) must already be included by the translation unit.
+#ifndef BALM_B200_PLPTR_TYPE  // element type of VOX_HESS::plptrs (bavoxel.hpp:28)
+#define BALM_B200_PLPTR_TYPE pcl::PointCloud<PointType>::Ptr
+#define BALM_B200_PLPTR_NEW (pcl::PointCloud<PointType>::Ptr(new pcl::PointCloud<PointType>()))
+#endif
 namespace balm_b200_shim {
 typedef Eigen::MatrixXd DenseMat;
 typedef Eigen::VectorXd DenseVec;
@@ -96,6 +102,8 @@ inline void pose_unpack(const double *o, IMUST &x) { std::memcpy(x.R, o, 9 * siz
 #ifndef BALM_B200_NO_WIN_SIZE
 static int win_size = 20;  // bavoxel.hpp:17
 #endif
+#define BALM_B200_PLPTR_TYPE std::shared_ptr<void>
+#define BALM_B200_PLPTR_NEW (std::shared_ptr<void>())
 #endif  // BALM_B200_WITH_EIGEN
 
 class VOX_HESS {
@@ -104,6 +112,7 @@ class VOX_HESS {
   std::vector<const PointCluster *> sig_vecs;
   std::vector<const std::vector<PointCluster> *> plvec_voxels;
   std::vector<double> coeffs, coeffs_back;
+  std::vector<BALM_B200_PLPTR_TYPE> plptrs;  // bavoxel.hpp:28 (one empty cloud per voxel, :49-50; unused by the BA)
 
   int device = 0;
   int precision = BALM_PREC_TENSOR;
@@ -120,12 +129,18 @@ class VOX_HESS {
     plvec_voxels.push_back(vec_orig);
     sig_vecs.push_back(fix);
     coeffs.push_back(coe);
+    plptrs.push_back(BALM_B200_PLPTR_NEW);
     dirty_ = true;
   }
 
-  // bavoxel.hpp:304-426
-  template <class Mat, class Vec>
-  void left_evaluate_acc2(const std::vector<IMUST> &xs, int head, int end, Mat &Hess, Vec &JacT, double &residual) {
+  // bavoxel.hpp:304-426. A plain member function on the reference's own dense types (Eigen::MatrixXd / VectorXd with
+  // Eigen), so that  &VOX_HESS::left_evaluate_acc2  binds -- the reference's divide_thread_left hands exactly that to
+  // std::thread with a voxel range per thread (bavoxel.hpp:1044-1047). A context owns one CUDA stream and is not
+  // re-entrant: concurrent calls are serialised here (each range is still evaluated on the whole GPU, in the order the
+  // threads arrive; the caller's ordered reduction of the per-thread results is untouched).
+  void left_evaluate_acc2(const std::vector<IMUST> &xs, int head, int end, balm_b200_shim::DenseMat &Hess,
+                          balm_b200_shim::DenseVec &JacT, double &residual) {
+    std::lock_guard<std::mutex> lock(mu_);
     balm_ctx *c = context((int)xs.size());
     const int n = 6 * (int)xs.size();
     balm_b200_shim::mat_resize(Hess, n);
@@ -137,6 +152,7 @@ class VOX_HESS {
 
   // bavoxel.hpp:428-470
   void evaluate_only_residual(const std::vector<IMUST> &xs, double &residual) {
+    std::lock_guard<std::mutex> lock(mu_);
     balm_ctx *c = context((int)xs.size());
     std::vector<double> poses = pack(xs);
     check(balm_residual(c, poses.data(), &residual));
@@ -145,7 +161,8 @@ class VOX_HESS {
   ~VOX_HESS() { if (ctx_) balm_destroy(ctx_); }
 
   // ---- shim internals ----
-  balm_ctx *context(int n_poses) {
+  std::mutex &mutex() { return mu_; }
+  balm_ctx *context(int n_poses) {  // callers hold mu_
     if (n_poses != win_size) {
       std::fprintf(stderr, "balm_b200: win_size (%d) must equal x_stats.size() (%d)\n", win_size, n_poses);
       std::abort();
@@ -195,6 +212,7 @@ class VOX_HESS {
   balm_ctx *ctx_ = nullptr;
   int n_poses_ = 0;
   bool dirty_ = true;
+  std::mutex mu_;
 };
 
 class BALM2 {
@@ -203,8 +221,8 @@ class BALM2 {
 
   // bavoxel.hpp:1025-1059. The 4-way std::thread split and ordered reduction happen inside the library
   // (CTAs / GPUs instead of threads); x_ab is unused there as well (:1096-1102).
-  template <class Mat, class Vec>
-  double divide_thread_left(std::vector<IMUST> &x_stats, VOX_HESS &voxhess, std::vector<IMUST> &x_ab, Mat &Hess, Vec &JacT) {
+  double divide_thread_left(std::vector<IMUST> &x_stats, VOX_HESS &voxhess, std::vector<IMUST> &x_ab,
+                            balm_b200_shim::DenseMat &Hess, balm_b200_shim::DenseVec &JacT) {
     (void)x_ab;
     double residual = 0;
     voxhess.left_evaluate_acc2(x_stats, 0, (int)voxhess.plvec_voxels.size(), Hess, JacT, residual);
@@ -221,6 +239,7 @@ class BALM2 {
 
   // bavoxel.hpp:1069-1166
   void damping_iter(std::vector<IMUST> &x_stats, VOX_HESS &voxhess) {
+    std::lock_guard<std::mutex> lock(voxhess.mutex());
     balm_ctx *c = voxhess.context((int)x_stats.size());
     balm_lm_opts o;
     balm_default_lm_opts(&o);  // u=0.01, v=2, 10 iterations, 1e-6, >=20 planes per pose: the reference constants

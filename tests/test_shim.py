@@ -17,6 +17,33 @@ def _build():
                            "-Wl,-rpath," + lib, "-ldl", "-lpthread", "-lrt"])
 
 
+EXE2 = os.path.join(ROOT, "tests", "shim_eigen_branch.bin")
+
+
+def _build_eigen_branch():
+    lib = os.path.join(ROOT, "balm_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++14", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "tests", "eigen_stub"),
+                           os.path.join(ROOT, "tests", "shim_eigen_branch.cpp"), "-o", EXE2, "-L" + lib, "-lbalm_b200",
+                           "-Wl,-rpath," + lib, "-ldl", "-lpthread", "-lrt"])
+
+
+def test_shim_eigen_branch_compiles_and_links():
+    """The BALM_B200_WITH_EIGEN branch (reference types: Eigen::MatrixXd / VectorXd / Matrix3d members) against a stand-in
+    for the few Eigen members it uses, and &VOX_HESS::left_evaluate_acc2 handed to std::thread as bavoxel.hpp:1047 does."""
+    _build_eigen_branch()
+    assert os.path.exists(EXE2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", [0, 1])
+def test_reference_divide_thread_left_runs_on_the_shim(prec):
+    _build_eigen_branch()
+    out = subprocess.run([EXE2, str(prec)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "shim_eigen_branch:" in out.stdout
+
+
 def test_shim_compiles_and_links():
     _build()
     assert os.path.exists(EXE)
