@@ -179,3 +179,22 @@ def test_empty_shard_is_registered_and_contributes_zero():
     H, g, r = c.evaluate(np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]), (5, 1)))
     assert r == 0 and not H.any() and not g.any()
     assert c.residual(np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]), (5, 1))) == 0
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_not_pd_pivot_is_reported_and_rejects_the_step(prec):
+    """A zero pivot (u = -1 makes every diagonal entry of H + u diag(H) exactly zero) must raise not_pd in balm_solve, and
+    inside the LM loop count as a rejected step (u *= v, poses untouched) -- the reference never checks its LDLT
+    (bavoxel.hpp:1114); a step that cannot be computed is the one thing the library refuses instead of following."""
+    import balm_b200
+    sc = scenes.make_scene(n_poses=9, n_planes=60, seed=72)
+    c = balm_b200.Context(9, 0, prec)
+    c.set_voxels(sc["row_ptr"], sc["pose_idx"], sc["obs10"], sc["coe"])
+    c.evaluate(sc["poses_init"])
+    dx, q1, bad = c.solve(-1.0)
+    assert bad
+    dx, q1, bad = c.solve(0.01)
+    assert not bad and np.isfinite(dx).all()
+    poses, tr, _ = c.damping_iter(sc["poses_init"], max_iter=1, u0=-1.0, min_planes_per_pose=0, gauge_mode=2)
+    assert len(tr) == 1 and tr[0]["not_pd"] and not tr[0]["accepted"] and tr[0]["u"] == -1.0
+    assert np.array_equal(poses, sc["poses_init"])                   # a rejected step leaves the poses alone (:1144-1149)
