@@ -108,6 +108,7 @@ __device__ __forceinline__ bool diag_factor(double (*S)[NB + 1], double (*Xs)[NB
           xr[q] -= l * xj;
         }
       }
+      __syncwarp();  // the mirror lanes 16..31 have read their copy of the block before it is overwritten
       if (lane < 16) {
 #pragma unroll
         for (int q = 0; q < 16; q++) {
