@@ -198,3 +198,23 @@ def test_not_pd_pivot_is_reported_and_rejects_the_step(prec):
     poses, tr, _ = c.damping_iter(sc["poses_init"], max_iter=1, u0=-1.0, min_planes_per_pose=0, gauge_mode=2)
     assert len(tr) == 1 and tr[0]["not_pd"] and not tr[0]["accepted"] and tr[0]["u"] == -1.0
     assert np.array_equal(poses, sc["poses_init"])                   # a rejected step leaves the poses alone (:1144-1149)
+
+
+@pytest.mark.parametrize("n_poses,n_planes", [(3, 12), (11, 40), (22, 60), (130, 60), (320, 40)])
+def test_solve_edge_sizes_vs_numpy(n_poses, n_planes):
+    """The persistent tile-DAG factorisation at sizes around its tile boundaries: n = 18 (one partial tile), 66 (one full
+    tile + 2 columns), 132, 780 (12 tiles + 12 columns: near and far worker groups, partial last block), 1920 (30 tiles)."""
+    import balm_b200
+    sc = scenes.make_scene(n_poses=n_poses, n_planes=n_planes, seed=73, pts_size=8)
+    c = balm_b200.Context(n_poses, 0, 0)
+    c.set_voxels(sc["row_ptr"], sc["pose_idx"], sc["obs10"], sc["coe"])
+    H, g, r = c.evaluate(sc["poses_init"])
+    for u in (0.01, 1.0):
+        dx, q1, bad = c.solve(u)
+        A = H + u * np.diag(np.diag(H))
+        ref = np.linalg.solve(A, -g)
+        assert not bad
+        assert np.abs(dx - ref).max() <= 1e-9 * max(1e-3, np.abs(ref).max()), (n_poses, u)
+        assert abs(q1 - 0.5 * ref @ (u * np.diag(H) * ref - g)) <= 1e-9 * abs(q1)
+    dx2, _, _ = c.solve(1.0)
+    assert np.array_equal(dx, dx2)                                    # bit-reproducible
