@@ -7,15 +7,18 @@ A "step" is one Levenberg-Marquardt iteration of BALM2::damping_iter (bavoxel.hp
   is the same amount of work whether the trial step is accepted or not.
 Workload (N=1): BASELINE config C3 -- 500 poses x 100 000 plane voxels, synthetic plane features of the
 benchmark_virtual shape (benchmark_virtual.cpp:547-606), every pose sees every plane, 40 points/observation.
-With --gpus G each rank holds its own 100k-voxel shard of one G*100k-voxel scene (weak scaling, BASELINE
-config C4 shape); the library all-reduces [H|g|r] with NCCL once per evaluation.
+With --gpus G each rank holds its own --voxels shard of one G*--voxels scene (weak scaling; --voxels 125000 --gpus 8 is
+BASELINE config C4), or --scaling strong cuts ONE --voxels problem into G shards; the library all-reduces the lower
+triangle of [H|g|r] with NCCL once per evaluation, and every multi-GPU run first checks a small sharded scene against
+the same scene on one GPU ("mgpu_parity").
 
-  value      : shard-iterations per second with the voxels already resident in HBM (G * K / t)
-  e2e        : the same through the host-buffer call (balm_set_voxels from pinned host arrays + damping_iter +
-               poses back), copies inside the timed region
+  value      : shard-iterations per second with the voxels already resident in HBM (G * K / t; strong: K / t)
+  e2e        : the same through the host-buffer call, per call: balm_set_voxels from pinned host arrays + a 10-iteration
+               damping_iter (the reference's cap) + poses back, copies inside the timed region
   roofline   : dominant kernel = the rank-3M symmetric update (SYRK, bavoxel.hpp:404-418 restated)
   cpu_baseline : the CPU oracle (port of the reference loop nest; Eigen/PCL/ROS are absent so the reference
-               itself cannot be built here) timed on a bounded voxel sample of the same workload
+               itself cannot be built here) timed on two bounded voxel samples of the same workload and extrapolated
+               with slope + intercept
 
   python bench.py --gpus N --steps K --warmup W [--impl reference] [--poses P --voxels M --precision fp64|tensor]
 """
@@ -238,7 +241,7 @@ def run_reference(args, rank, world):
     No balm_b200 code runs."""
     if rank != 0:
         return
-    n, m = args.poses, args.voxels * (1 if args.scaling == "strong" else 1)
+    n, m = args.poses, args.voxels
     arm = CpuArm(n, args.cpu_sample_small, args.cpu_sample_large)
     wall, its, detail = [], [], None
     for i in range(args.warmup + args.steps):
