@@ -126,6 +126,21 @@ class Context:
         self.M = M.value
         return M.value, K.value
 
+    def append_scan(self, xyz, poses12, slot):
+        """Associates a new scan (body-frame points) with the voxel set in HBM: observation in pose slot `slot`, every voxel
+        re-judged as recut / judge_eigen do. -> (n_voxels, n_obs, n_points_matched)."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        poses12 = np.ascontiguousarray(poses12, dtype=np.float64)
+        M, K, m = C.c_int64(), C.c_int64(), C.c_int64()
+        L.check(L.lib().balm_append_scan(self._h, len(xyz), _p(xyz), _p(poses12), int(slot), C.byref(M), C.byref(K), C.byref(m)))
+        self.M = M.value
+        return M.value, K.value, m.value
+
+    def download_keys(self):
+        keys = np.zeros(self.M, dtype=np.uint64)
+        L.check(L.lib().balm_download_keys(self._h, _p(keys)))
+        return keys
+
     def download_fix(self):
         fix = np.zeros((self.M, 10))
         L.check(L.lib().balm_download_fix(self._h, _p(fix)))

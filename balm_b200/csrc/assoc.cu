@@ -36,6 +36,9 @@ __device__ __forceinline__ long long ref_voxel_index(double w, double vs) {
   return (long long)loc;                 // (int64_t) cast truncates toward zero              (:1184)
 }
 
+// 63-bit key of a world point: root voxel (cut_voxel) + the octants cut_func would choose at layers 1 and 2
+__device__ __forceinline__ unsigned long long world_point_key(const double *w, const AssocParams &p, int *bad);
+
 __global__ void point_key_kernel(const float *xyz, const int *frame, const double *poses, int n_poses, int64_t n,
                                  AssocParams p, unsigned long long *key, int *bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -48,6 +51,10 @@ __global__ void point_key_kernel(const float *xyz, const int *frame, const doubl
   double w[3];
 #pragma unroll
   for (int a = 0; a < 3; a++) w[a] = r[a * 3] * b[0] + r[a * 3 + 1] * b[1] + r[a * 3 + 2] * b[2] + t[a];
+  key[i] = world_point_key(w, p, bad);
+}
+
+__device__ __forceinline__ unsigned long long world_point_key(const double *w, const AssocParams &p, int *bad) {
   unsigned long long k = 0;
   int oct1 = 0, oct2 = 0;
   const float quater = (float)(p.voxel_size / 4.0);  // ot->quater_length (:1216)
@@ -63,7 +70,7 @@ __global__ void point_key_kernel(const float *xyz, const int *frame, const doubl
     oct1 = (oct1 << 1) | b1;
     oct2 = (oct2 << 1) | b2;
   }
-  key[i] = (k << 6) | (unsigned long long)(oct1 << 3) | (unsigned long long)oct2;
+  return (k << 6) | (unsigned long long)(oct1 << 3) | (unsigned long long)oct2;
 }
 
 __global__ void iota_kernel(int *v, int64_t n) {
@@ -397,6 +404,14 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   c->launches += 12;
+  // the voxel keys (ascending) and the parameters stay with the context: balm_append_scan / balm_marginalize need them
+  cudaFree(c->vox_key);
+  c->vox_key = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&c->vox_key, sizeof(unsigned long long) * (size_t)nleaf));
+  CUDA_TRY(cudaMemcpy(c->vox_key, lkey2, sizeof(unsigned long long) * (size_t)nleaf, cudaMemcpyDeviceToDevice));
+  c->has_keys = true;
+  c->assoc_voxel_size = voxel_size; c->assoc_layer_limit = layer_limit; c->assoc_min_ps = min_ps;
+  for (int q = 0; q < 3; q++) c->assoc_eig[q] = eig3[q];
   // the pool's destructor frees every scratch buffer (level tables included)
   *M_out = nleaf;
   *K_out = K;
@@ -503,11 +518,12 @@ __global__ void marg_emit_kernel(const long long *row_ptr, const int *pose_idx, 
                                  const double *fix /*SoA [10][M] or null*/, int64_t M, const double *poses, int mg,
                                  const int *keep, const int *vscan, const int *oscan, long long *row_ptr_out,
                                  int *pose_idx_out, double *obs10_out, double *fix10_out, double *coe_out, int64_t Mout,
-                                 int64_t Kout) {
+                                 int64_t Kout, const unsigned long long *key_in, unsigned long long *key_out) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v == 0) row_ptr_out[Mout] = Kout;
   if (v >= M || !keep[v]) return;
   const int nv = vscan[v];
+  if (key_in) key_out[nv] = key_in[v];
   long long o = oscan[v];
   row_ptr_out[nv] = o;
   double f[10];
@@ -537,6 +553,18 @@ __global__ void marg_emit_kernel(const long long *row_ptr, const int *pose_idx, 
   coe_out[nv] = pts;
 }
 }  // namespace
+
+// after a re-registration: the compacted keys of the new voxel set (or none)
+static int install_keys(balm_ctx *c, const unsigned long long *keys_dev, int64_t M, bool have) {
+  cudaFree(c->vox_key);
+  c->vox_key = nullptr;
+  c->has_keys = false;
+  if (!have) return BALM_OK;
+  CUDA_TRY(cudaMalloc((void **)&c->vox_key, sizeof(unsigned long long) * (size_t)M));
+  CUDA_TRY(cudaMemcpy(c->vox_key, keys_dev, sizeof(unsigned long long) * (size_t)M, cudaMemcpyDeviceToDevice));
+  c->has_keys = true;
+  return BALM_OK;
+}
 
 int marginalize_build(balm_ctx *c, int mg, const double *poses_dev, int min_ps, int64_t *M_out, int64_t *K_out,
                       int (*reg)(balm_ctx *, int64_t, const int64_t *, const int32_t *, const double *, const double *,
@@ -568,12 +596,203 @@ int marginalize_build(balm_ctx *c, int mg, const double *poses_dev, int min_ps, 
   double *ob = nullptr, *fx = nullptr, *co = nullptr;
   ATRY(pool.get(&rp, (size_t)Mout + 1)); ATRY(pool.get(&pi, (size_t)Kout)); ATRY(pool.get(&ob, (size_t)Kout * 10));
   ATRY(pool.get(&fx, (size_t)Mout * 10)); ATRY(pool.get(&co, (size_t)Mout));
+  unsigned long long *keys_out = nullptr;
+  const bool had_keys = c->has_keys && c->vox_key;
+  if (had_keys) ATRY(pool.get(&keys_out, (size_t)Mout));
   marg_emit_kernel<<<gb, 128, 0, st>>>(c->row_ptr, c->pose_idx, c->obs, c->Kp, c->fix, M, poses_dev, mg, keep, vscan, oscan, rp,
-                                       pi, ob, fx, co, Mout, Kout);
+                                       pi, ob, fx, co, Mout, Kout, had_keys ? c->vox_key : nullptr, keys_out);
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   c->launches += 4;
   if (Mout < 1) { balm_set_error("balm_marginalize: no voxel is left with two observing scans"); return BALM_ERR_INVALID; }
   // re-register from the device arrays (copies them, transposes the observations, rebuilds the pose-major lists)
-  return reg(c, Mout, (const int64_t *)rp, pi, ob, fx, co, Kout);
+  ATRY(reg(c, Mout, (const int64_t *)rp, pi, ob, fx, co, Kout));
+  return install_keys(c, keys_out, Mout, had_keys);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Appending a scan to the voxel set in HBM (the other half of the sliding window).
+// Reference: cut_voxel pushes the new scan's points into the root voxels (bavoxel.hpp:1170-1223), recut hands them down
+// to the leaves (cut_func(win_count-1) on split nodes, :737-776) and RE-JUDGES every leaf with its fix cluster and all
+// window clusters (judge_eigen, :654-699): still planar with more than min_ps window points -> pushed again with the new
+// observation; otherwise the reference splits it further or freezes it. Here: every new point finds the leaf that contains
+// it through the stored keys (the same arithmetic as balm_cut_voxels), its body-frame moments become a new observation
+// in pose slot `slot`, and every voxel is re-judged from fix + all its clusters transformed by the current poses; a voxel
+// that fails (not planar any more, too few points, fewer than two scans) is dropped. NOT done (documented): creating new
+// roots / new leaves from points that fall outside the existing planes, and re-splitting a leaf that stopped being planar
+// -- both appear at the next full balm_cut_voxels.
+namespace {
+__global__ void append_match_kernel(const float *xyz, const double *pose12, int64_t n, AssocParams p,
+                                    const unsigned long long *vox_key, int M, unsigned *vid1, int *bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r[9], t[3];
+  load_pose(pose12, r, t);
+  const double b[3] = {(double)xyz[3 * i], (double)xyz[3 * i + 1], (double)xyz[3 * i + 2]};
+  double w[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) w[a] = r[a * 3] * b[0] + r[a * 3 + 1] * b[1] + r[a * 3 + 2] * b[2] + t[a];
+  int dummy = 0;
+  (void)bad;
+  const unsigned long long k = world_point_key(w, p, &dummy);
+  int v = find_key(vox_key, M, k | 63ull);            // a layer-0 leaf (the whole root voxel is one plane)
+  if (v < 0) v = find_key(vox_key, M, k | 7ull);      // a layer-1 leaf
+  if (v < 0) v = find_key(vox_key, M, k);             // a layer-2 leaf
+  vid1[i] = (unsigned)(v + 1);                        // 0 = the point falls into no registered plane voxel
+}
+// one thread per voxel: the new scan's body-frame cluster (points in their original order)
+__global__ void append_cluster_kernel(const float *xyz, const unsigned *vid_sorted, const int *idx_sorted, int64_t n, int M,
+                                      double *newobs /*[M][10]*/) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= M) return;
+  const unsigned want = (unsigned)(v + 1);
+  int64_t lo = 0, hi = n;
+  while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (vid_sorted[m] < want) lo = m + 1; else hi = m; }
+  double B[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = lo; i < n && vid_sorted[i] == want; i++) {
+    const int j = idx_sorted[i];
+    const double x = xyz[3 * j], y = xyz[3 * j + 1], z = xyz[3 * j + 2];
+    B[0] += x * x; B[1] += x * y; B[2] += x * z; B[3] += y * y; B[4] += y * z; B[5] += z * z;
+    B[6] += x; B[7] += y; B[8] += z; B[9] += 1.0;
+  }
+#pragma unroll
+  for (int q = 0; q < 10; q++) newobs[(size_t)v * 10 + q] = B[q];
+}
+// one thread per voxel: judge_eigen on fix + every window cluster (old ones and the new one) at the current poses
+__global__ void append_judge_kernel(const long long *row_ptr, const int *pose_idx, const double *obs, int64_t Kp,
+                                    const double *fix, int64_t M, const double *poses, const double *newobs, int slot,
+                                    const unsigned long long *vox_key, AssocParams p, int *keep, int *cnt, int *bad) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= M) return;
+  double W[10];
+  for (int q = 0; q < 10; q++) W[q] = fix ? fix[q * M + v] : 0.0;
+  double pts = 0.0;
+  int k = 0;
+  for (long long s = row_ptr[v]; s < row_ptr[v + 1]; s++) {
+    double ob[10];
+    for (int q = 0; q < 10; q++) ob[q] = obs[q * Kp + s];
+    double r[9], t[3];
+    load_pose(poses + 12 * pose_idx[s], r, t);
+    const WC w = world_cluster(ob, r, t);
+    W[0] += w.p00; W[1] += w.p01; W[2] += w.p02; W[3] += w.p11; W[4] += w.p12; W[5] += w.p22;
+    W[6] += w.v0; W[7] += w.v1; W[8] += w.v2; W[9] += w.n;
+    pts += ob[9];
+    k++;
+    if (pose_idx[s] >= slot) atomicOr(bad, 1);  // the new scan must take a slot above every scan already in the voxel
+  }
+  const double *nb = newobs + (size_t)v * 10;
+  if (nb[9] > 0.0) {
+    double r[9], t[3];
+    load_pose(poses + 12 * slot, r, t);
+    const WC w = world_cluster(nb, r, t);
+    W[0] += w.p00; W[1] += w.p01; W[2] += w.p02; W[3] += w.p11; W[4] += w.p12; W[5] += w.p22;
+    W[6] += w.v0; W[7] += w.v1; W[8] += w.v2; W[9] += w.n;
+    pts += nb[9];
+    k++;
+  }
+  const double inv = 1.0 / W[9];
+  const double c0 = W[6] * inv, c1 = W[7] * inv, c2 = W[8] * inv;
+  double lam[3], u0[3], u1[3], u2[3];
+  eig3_jacobi(W[0] * inv - c0 * c0, W[1] * inv - c0 * c1, W[2] * inv - c0 * c2, W[3] * inv - c1 * c1,
+              W[4] * inv - c1 * c2, W[5] * inv - c2 * c2, lam, u0, u1, u2);
+  const unsigned long long key = vox_key[v];
+  const int layer = (key & 63ull) == 63ull ? 0 : ((key & 7ull) == 7ull ? 1 : 2);
+  const bool planar = lam[0] / lam[1] < p.eig[layer];                     // judge_eigen (:665,697)
+  const int kp = (planar && (int)pts > p.min_ps && k >= 2) ? 1 : 0;       // recut :755-757, push_voxel :37
+  keep[v] = kp;
+  cnt[v] = kp ? k : 0;
+}
+__global__ void append_emit_kernel(const long long *row_ptr, const int *pose_idx, const double *obs, int64_t Kp,
+                                   const double *fix, const double *coe, int64_t M, const double *newobs, int slot,
+                                   const int *keep, const int *vscan, const int *oscan, const unsigned long long *key_in,
+                                   long long *row_ptr_out, int *pose_idx_out, double *obs10_out, double *fix10_out,
+                                   double *coe_out, unsigned long long *key_out, int64_t Mout, int64_t Kout) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v == 0) row_ptr_out[Mout] = Kout;
+  if (v >= M || !keep[v]) return;
+  const int nv = vscan[v];
+  long long o = oscan[v];
+  row_ptr_out[nv] = o;
+  key_out[nv] = key_in[v];
+  for (long long s = row_ptr[v]; s < row_ptr[v + 1]; s++, o++) {
+    for (int q = 0; q < 10; q++) obs10_out[o * 10 + q] = obs[q * Kp + s];
+    pose_idx_out[o] = pose_idx[s];
+  }
+  const double *nb = newobs + (size_t)v * 10;
+  if (nb[9] > 0.0) {
+    for (int q = 0; q < 10; q++) obs10_out[o * 10 + q] = nb[q];
+    pose_idx_out[o] = slot;
+  }
+  for (int q = 0; q < 10; q++) fix10_out[(size_t)nv * 10 + q] = fix ? fix[q * M + v] : 0.0;
+  coe_out[nv] = coe[v] + nb[9];  // push_voxel: coe = sum of N over the window (:42-44)
+}
+}  // namespace
+
+int append_scan_build(balm_ctx *c, int64_t n, const float *xyz_h, const double *poses_dev, int slot, int64_t *M_out,
+                      int64_t *K_out, int64_t *matched_out,
+                      int (*reg)(balm_ctx *, int64_t, const int64_t *, const int32_t *, const double *, const double *,
+                                 const double *, int64_t)) {
+  const int64_t M = c->M;
+  cudaStream_t st = c->stream;
+  ScratchPool pool;
+  AssocParams P{c->assoc_voxel_size, c->assoc_layer_limit, c->assoc_min_ps, {c->assoc_eig[0], c->assoc_eig[1], c->assoc_eig[2]}};
+  float *xyz = nullptr;
+  unsigned *vid = nullptr, *vid2 = nullptr;
+  int *idx = nullptr, *idx2 = nullptr, *keep = nullptr, *cnt = nullptr, *vscan = nullptr, *oscan = nullptr, *bad = nullptr;
+  double *newobs = nullptr;
+  ATRY(pool.get(&xyz, (size_t)3 * n)); ATRY(pool.get(&vid, (size_t)n)); ATRY(pool.get(&vid2, (size_t)n));
+  ATRY(pool.get(&idx, (size_t)n)); ATRY(pool.get(&idx2, (size_t)n)); ATRY(pool.get(&newobs, (size_t)M * 10));
+  ATRY(pool.get(&keep, (size_t)M)); ATRY(pool.get(&cnt, (size_t)M)); ATRY(pool.get(&vscan, (size_t)M)); ATRY(pool.get(&oscan, (size_t)M));
+  ATRY(pool.get(&bad, 1));
+  CUDA_TRY(cudaMemcpyAsync(xyz, xyz_h, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int), st));
+  const unsigned gp = (unsigned)((n + 255) / 256), gv = (unsigned)((M + 127) / 128);
+  append_match_kernel<<<gp, 256, 0, st>>>(xyz, poses_dev + 12 * slot, n, P, c->vox_key, (int)M, vid, bad);
+  iota_kernel<<<gp, 256, 0, st>>>(idx, n);
+  int bits = 1;
+  while ((1ll << bits) <= M) bits++;
+  size_t tb = 0, tb2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, vid, vid2, idx, idx2, (int)n, 0, bits, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb2, keep, vscan, (int)M, st);
+  tb = std::max(tb, tb2);
+  char *tmp = nullptr;
+  ATRY(pool.get(&tmp, tb));
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, vid, vid2, idx, idx2, (int)n, 0, bits, st));  // stable: point order kept
+  append_cluster_kernel<<<gv, 128, 0, st>>>(xyz, vid2, idx2, n, (int)M, newobs);
+  append_judge_kernel<<<gv, 128, 0, st>>>(c->row_ptr, c->pose_idx, c->obs, c->Kp, c->fix, M, poses_dev, newobs, slot, c->vox_key, P,
+                                          keep, cnt, bad);
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tb, keep, vscan, (int)M, st));
+  CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, oscan, (int)M, st));
+  int last[5] = {0, 0, 0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(&last[0], keep + M - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&last[1], vscan + M - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&last[2], cnt + M - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&last[3], oscan + M - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&last[4], bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (last[4]) { balm_set_error("balm_append_scan: `slot` must be above every scan already observing the voxels"); return BALM_ERR_INVALID; }
+  const int64_t Mout = (int64_t)last[0] + last[1], Kout = (int64_t)last[2] + last[3];
+  if (Mout < 1) { balm_set_error("balm_append_scan: no plane voxel survives the re-judgement"); return BALM_ERR_INVALID; }
+  if (matched_out) {  // points that fell into a registered voxel: n minus the leading zeros of the sorted ids
+    std::vector<unsigned> h((size_t)n);
+    CUDA_TRY(cudaMemcpy(h.data(), vid2, sizeof(unsigned) * (size_t)n, cudaMemcpyDeviceToHost));
+    *matched_out = n - (std::upper_bound(h.begin(), h.end(), 0u) - h.begin());
+  }
+  long long *rp = nullptr;
+  int *pi = nullptr;
+  double *ob = nullptr, *fx = nullptr, *co = nullptr;
+  unsigned long long *keys_out = nullptr;
+  ATRY(pool.get(&rp, (size_t)Mout + 1)); ATRY(pool.get(&pi, (size_t)Kout)); ATRY(pool.get(&ob, (size_t)Kout * 10));
+  ATRY(pool.get(&fx, (size_t)Mout * 10)); ATRY(pool.get(&co, (size_t)Mout)); ATRY(pool.get(&keys_out, (size_t)Mout));
+  append_emit_kernel<<<gv, 128, 0, st>>>(c->row_ptr, c->pose_idx, c->obs, c->Kp, c->fix, c->coe, M, newobs, slot, keep, vscan, oscan,
+                                         c->vox_key, rp, pi, ob, fx, co, keys_out, Mout, Kout);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 8;
+  *M_out = Mout;
+  *K_out = Kout;
+  const bool any_fix = c->fix != nullptr;
+  ATRY(reg(c, Mout, (const int64_t *)rp, pi, ob, any_fix ? fx : nullptr, co, Kout));
+  return install_keys(c, keys_out, Mout, true);
 }

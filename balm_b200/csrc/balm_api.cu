@@ -71,6 +71,11 @@ static void free_problem(balm_ctx *c) {
   c->M = c->K = c->Kp = 0;
   c->registered = false;
 }
+static void drop_keys(balm_ctx *c) {  // a voxel set registered from arrays carries no octree keys
+  cudaFree(c->vox_key);
+  c->vox_key = nullptr;
+  c->has_keys = false;
+}
 
 static int alloc_problem_arrays(balm_ctx *c, int64_t M, int64_t K, bool with_fix) {
   // A window of the same shape as the previous one (the common case when BA runs scan after scan, and what every
@@ -210,7 +215,7 @@ extern "C" int balm_destroy(balm_ctx *c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaFree(c->poses); cudaFree(c->poses_trial); cudaFree(c->H); cudaFree(c->A); cudaFree(c->W);
   cudaFree(c->dx); cudaFree(c->dvec); cudaFree(c->scal); cudaFree(c->flags); cudaFree(c->accum); cudaFree(c->accum_batch);
-  cudaFree(c->res_part); cudaFree(c->planes); cudaFree(c->Xinv); cudaFree(c->dinv); cudaFree(c->sol); cudaFree(c->ysol);
+  cudaFree(c->vox_key); cudaFree(c->res_part); cudaFree(c->planes); cudaFree(c->Xinv); cudaFree(c->dinv); cudaFree(c->sol); cudaFree(c->ysol);
   cudaFree(c->Hpack); cudaFree(c->dval); cudaFree(c->rres); cudaFree(c->rdelta); cudaFree(c->dag_flags);
   if (c->solve_graph) cudaGraphExecDestroy((cudaGraphExec_t)c->solve_graph);
   cudaFreeHost(c->h_scal); cudaFreeHost(c->h_flags);
@@ -341,6 +346,7 @@ extern "C" int balm_set_voxels(balm_ctx *c, int64_t M, const int64_t *row_ptr, c
     return BALM_ERR_INVALID;
   }
   CUDA_TRY(cudaSetDevice(c->device));
+  drop_keys(c);
   if (M == 0) return register_empty(c);  // a rank of a multi-GPU job whose shard holds no voxels still joins every collective
   const int64_t K = row_ptr[M];
   if (row_ptr[0] != 0 || K < M) { balm_set_error("balm_set_voxels: bad row_ptr"); return BALM_ERR_INVALID; }
@@ -379,6 +385,7 @@ extern "C" int balm_set_voxels_dev(balm_ctx *c, int64_t M, const int64_t *row_pt
     if (ends[0] != 0 || ends[1] != K) { balm_set_error("balm_set_voxels_dev: row_ptr[0] != 0 or row_ptr[M] != n_obs"); return BALM_ERR_INVALID; }
     if (K >= ((int64_t)1 << 31)) { balm_set_error("balm_set_voxels_dev: more than 2^31 observations per GPU"); return BALM_ERR_UNSUPPORTED; }
   }
+  drop_keys(c);
   TRY(alloc_problem_arrays(c, M, K, fix10_dev != nullptr));
   CUDA_TRY(cudaMemcpyAsync(c->row_ptr, row_ptr_dev, sizeof(int64_t) * (M + 1), cudaMemcpyDeviceToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(c->pose_idx, pose_idx_dev, sizeof(int32_t) * K, cudaMemcpyDeviceToDevice, c->stream));
@@ -467,6 +474,7 @@ extern "C" int balm_synth_virtual(balm_ctx *c, int64_t M, int64_t first_voxel, i
   synth_host_poses(c->N, seed, gt.data(), init.data());
   if (poses_gt) memcpy(poses_gt, gt.data(), sizeof(double) * gt.size());
   if (poses_init) memcpy(poses_init, init.data(), sizeof(double) * init.size());
+  drop_keys(c);
   TRY(alloc_problem_arrays(c, M, K, false));
   CUDA_TRY(cudaMemcpyAsync(c->poses_trial, gt.data(), sizeof(double) * gt.size(), cudaMemcpyHostToDevice, c->stream));
   TRY(launch_synth(c, M, first_voxel, pts, noise, range, seed, c->poses_trial));
@@ -824,6 +832,34 @@ extern "C" int balm_marginalize(balm_ctx *c, int mg_size, const double *poses12,
   TRY(marginalize_build(c, mg_size, c->poses, min_ps, &M, &K, balm_set_voxels_dev));
   if (n_voxels_out) *n_voxels_out = M;
   if (n_obs_out) *n_obs_out = K;
+  return BALM_OK;
+}
+int append_scan_build(balm_ctx *c, int64_t n, const float *xyz_h, const double *poses_dev, int slot, int64_t *M_out,
+                      int64_t *K_out, int64_t *matched_out,
+                      int (*reg)(balm_ctx *, int64_t, const int64_t *, const int32_t *, const double *, const double *,
+                                 const double *, int64_t));
+extern "C" int balm_append_scan(balm_ctx *c, int64_t n_points, const float *xyz, const double *poses12, int slot,
+                                int64_t *n_voxels_out, int64_t *n_obs_out, int64_t *n_matched_out) {
+  if (!c || !xyz || !poses12 || n_points < 1 || n_points >= (1ll << 31) || slot < 0 || slot >= c->N) {
+    balm_set_error("balm_append_scan: bad arguments");
+    return BALM_ERR_INVALID;
+  }
+  if (!c->registered || c->M < 1 || !c->has_keys) {
+    balm_set_error("balm_append_scan: needs a voxel set produced by balm_cut_voxels (octree keys)");
+    return BALM_ERR_INVALID;
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(c->poses, poses12, sizeof(double) * 12 * c->N, cudaMemcpyHostToDevice, c->stream));
+  int64_t M = 0, K = 0;
+  TRY(append_scan_build(c, n_points, xyz, c->poses, slot, &M, &K, n_matched_out, balm_set_voxels_dev));
+  if (n_voxels_out) *n_voxels_out = M;
+  if (n_obs_out) *n_obs_out = K;
+  return BALM_OK;
+}
+extern "C" int balm_download_keys(balm_ctx *c, uint64_t *keys) {
+  if (!c || !keys || !c->has_keys) { balm_set_error("balm_download_keys: the voxel set carries no octree keys"); return BALM_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpy(keys, c->vox_key, sizeof(uint64_t) * (size_t)c->M, cudaMemcpyDeviceToHost));
   return BALM_OK;
 }
 extern "C" int balm_download_fix(balm_ctx *c, double *fix10) {

@@ -57,6 +57,12 @@ struct balm_ctx {
   int min_planes = 0;             // min over poses of #voxels observing it (precheck, bavoxel.hpp:1071-1085)
   int *planes = nullptr;          // [2][N] device: this rank's per-pose voxel counts | their all-reduced sum
   bool registered = false;        // a voxel set (possibly empty: a rank whose shard has no voxels) is registered
+  unsigned long long *vox_key = nullptr;  // [M] 63-bit octree key of every voxel (ascending) when the set came from
+                                          // balm_cut_voxels: lets balm_append_scan find the leaf a new point falls into
+  bool has_keys = false;
+  double assoc_voxel_size = 1.0;  // association parameters of that call
+  int assoc_layer_limit = 2, assoc_min_ps = 15;
+  double assoc_eig[3] = {1.0 / 16, 1.0 / 16, 1.0 / 16};
 
   // ---- optimiser state (device) ----
   double *poses = nullptr, *poses_trial = nullptr;  // [12N]

@@ -146,6 +146,20 @@ int balm_cut_voxels(balm_ctx *ctx, int64_t n_points, const float *xyz, const int
 int balm_marginalize(balm_ctx *ctx, int mg_size, const double *poses12, int min_ps, int64_t *n_voxels_out,
                      int64_t *n_obs_out);
 int balm_download_fix(balm_ctx *ctx, double *fix10);
+/* The other half of the sliding window: a NEW scan is associated with the voxel set already in HBM (which must come from
+ * balm_cut_voxels: it carries the 63-bit octree key of every voxel). Every point (xyz: n_points x 3 float32, body frame)
+ * is transformed by poses12[slot], finds the plane leaf that contains it with the arithmetic of cut_voxel / cut_func
+ * (bavoxel.hpp:1170-1223, 700-735), and the body-frame moments of a leaf's new points become its observation in pose
+ * slot `slot` (which must lie above every scan already in the window); then EVERY voxel is re-judged as recut does
+ * (bavoxel.hpp:737-776 -> judge_eigen :654-699) from its fix cluster and all its clusters transformed by poses12 (N x 12):
+ * still planar (eigen ratio below the threshold of its layer), more than min_ps window points, at least two scans ->
+ * kept with coe = window points; otherwise dropped. Not done here (it happens at the next full balm_cut_voxels): new
+ * roots / leaves from points outside the registered planes, re-splitting a leaf that stopped being planar.
+ * n_matched_out: points that fell into a registered voxel. balm_download_keys copies the M voxel keys
+ * ([root x|y|z biased by 2^18, 19 bits each | octant at layer 1 | octant at layer 2], 7 = not split). */
+int balm_append_scan(balm_ctx *ctx, int64_t n_points, const float *xyz, const double *poses12, int slot,
+                     int64_t *n_voxels_out, int64_t *n_obs_out, int64_t *n_matched_out);
+int balm_download_keys(balm_ctx *ctx, uint64_t *keys);
 
 /* Pose-covariance propagation of the consistency experiment:
  *   Rcov_raw = sum over observations of  Ls c_cov Ls^T      -- VOX_HESS::left_jacobian_point + BALM2::multi_second

@@ -161,3 +161,74 @@ def marginalize_ref(n_poses, row_ptr, pose_idx, obs10, fix10, poses12, mg_size, 
         co.append(float(pts))
     return (np.array(rp, dtype=np.int64), np.array(pi, dtype=np.int32), np.array(ob).reshape(-1, 10),
             np.array(fx).reshape(-1, 10), np.array(co))
+
+
+def point_keys(world, voxel_size):
+    """Full 63-bit keys of world points: root index (cut_voxel) + the octants cut_func chooses at layers 1 and 2 with the
+    reference's float32 centres (bavoxel.hpp:1213-1216, 700-735). -> (root n x 3, oct1 n, oct2 n)."""
+    root = root_index(world, voxel_size)
+    c0 = ((0.5 + root) * voxel_size).astype(np.float32)
+    quater = np.float32(voxel_size / 4.0)
+    b1 = (world > c0.astype(np.float64)).astype(np.int64)
+    c1 = c0 + (2 * b1 - 1).astype(np.float32) * quater
+    b2 = (world > c1.astype(np.float64)).astype(np.int64)
+    return root, 4 * b1[:, 0] + 2 * b1[:, 1] + b1[:, 2], 4 * b2[:, 0] + 2 * b2[:, 1] + b2[:, 2]
+
+
+def append_scan_ref(keys, row_ptr, pose_idx, obs10, fix10, coe, points_body, poses12, slot, **kw):
+    """numpy restatement of balm_append_scan: the new scan's points find their plane leaf (cut_voxel + cut_func), their
+    body-frame moments become the leaf's observation in pose slot `slot`, and every leaf is re-judged as recut does
+    (bavoxel.hpp:737-776 -> judge_eigen :654-699): fix_point + all window clusters transformed by the current poses must be
+    planar (eigen ratio below the layer's threshold), hold more than min_ps window points and be seen by >= 2 scans.
+    -> keys, row_ptr, pose_idx, obs10, fix10, coe of the leaves that are pushed again, and the number of matched points."""
+    o = dict(DEFAULTS)
+    o.update(kw)
+    vs, min_ps = o["voxel_size"], o["min_ps"]
+    keymap = {int(k): a for a, k in enumerate(keys)}
+    R = poses12[slot][:9].reshape(3, 3).T
+    t = poses12[slot][9:12]
+    world = points_body @ R.T + t
+    root, o1, o2 = point_keys(world, vs)
+    new_pts = {}
+    matched = 0
+    for i in range(len(points_body)):
+        for cand in (node_key(root[i], 7, 7), node_key(root[i], int(o1[i]), 7), node_key(root[i], int(o1[i]), int(o2[i]))):
+            a = keymap.get(cand)
+            if a is not None:
+                new_pts.setdefault(a, []).append(points_body[i])
+                matched += 1
+                break
+    out_k, rp, pi, ob, fx, co = [], [0], [], [], [], []
+    for a, k in enumerate(keys):
+        rows = [(int(pose_idx[s]), np.array(obs10[s], dtype=np.float64)) for s in range(row_ptr[a], row_ptr[a + 1])]
+        if a in new_pts:
+            x = np.array(new_pts[a])
+            P = x.T @ x
+            v = x.sum(0)
+            assert all(p < slot for p, _ in rows)
+            rows.append((slot, np.array([P[0, 0], P[0, 1], P[0, 2], P[1, 1], P[1, 2], P[2, 2], v[0], v[1], v[2], float(len(x))])))
+        fix = np.zeros(10) if fix10 is None else np.array(fix10[a], dtype=np.float64)
+        W = fix.copy()
+        for p, c in rows:                                               # covMat = fix_point + sum sig_tran (:656-658)
+            Rp = poses12[p][:9].reshape(3, 3).T
+            tp = poses12[p][9:12]
+            Pm = np.array([[c[0], c[1], c[2]], [c[1], c[3], c[4]], [c[2], c[4], c[5]]])
+            Rv = Rp @ c[6:9]
+            Pw = Rp @ Pm @ Rp.T + np.outer(Rv, tp) + np.outer(tp, Rv) + c[9] * np.outer(tp, tp)
+            W += np.array([Pw[0, 0], Pw[0, 1], Pw[0, 2], Pw[1, 1], Pw[1, 2], Pw[2, 2], *(Rv + c[9] * tp), c[9]])
+        cen = W[6:9] / W[9]
+        cov = np.array([[W[0], W[1], W[2]], [W[1], W[3], W[4]], [W[2], W[4], W[5]]]) / W[9] - np.outer(cen, cen)
+        lam = np.linalg.eigvalsh(cov)
+        layer = 0 if (int(k) & 63) == 63 else (1 if (int(k) & 7) == 7 else 2)
+        pts = sum(c[9] for _, c in rows)
+        if not (lam[0] / lam[1] < float(np.float32(o["eigen_value_array"][layer]))) or int(pts) <= min_ps or len(rows) < 2:
+            continue
+        for p, c in rows:
+            pi.append(p)
+            ob.append(c)
+        rp.append(len(pi))
+        out_k.append(int(k))
+        fx.append(fix)
+        co.append(float(pts))
+    return (np.array(out_k, dtype=np.int64), np.array(rp, dtype=np.int64), np.array(pi, dtype=np.int32),
+            np.array(ob).reshape(-1, 10), np.array(fx).reshape(-1, 10), np.array(co), matched)

@@ -37,3 +37,60 @@ def test_marginalize_matches_reference_restatement(with_fix, drop, mg):
     assert abs(r - ro) <= 1e-12 * abs(ro) and np.abs(g - go).max() <= 1e-10 * np.abs(go).max()
     assert np.abs(H - Ho).max() <= 1e-9 * np.abs(Ho).max()
     assert abs(c.residual(shifted) - o.residual(shifted)) <= 1e-12 * abs(ro)
+
+
+def test_sliding_window_on_the_device_matches_the_restatement():
+    """The whole sliding-window step with nothing leaving HBM: associate a window of scans
+    (balm_cut_voxels), optimise, retire the two oldest scans into the fix clusters (balm_marginalize), associate a NEW
+    scan with the voxels already there (balm_append_scan: leaf lookup through the octree keys + recut's re-judgement),
+    optimise again -- against assoc_ref.cut_voxels / marginalize_ref / append_scan_ref step by step."""
+    import balm_b200
+    N, mg = 10, 2
+    pts, frs, poses = assoc_ref.synthetic_scans(n_poses=N + mg, pts_per_scan=5000, seed=13)
+    poses12_all = scenes.pack_poses([r for r, _ in poses], [p for _, p in poses])
+    win = frs < N                                               # the first N scans fill the window
+    c = balm_b200.Context(N, 0, 0)
+    kw = dict(voxel_size=2.0, layer_limit=2, min_ps=15, eigen_value_array=(1 / 16, 1 / 16, 1 / 16))
+    M0, K0 = c.cut_voxels(pts[win].astype(np.float32), frs[win], poses12_all[:N], **kw)
+    rp, pi, ob, co, keys = assoc_ref.cut_voxels(pts[win], frs[win], poses[:N], **kw)
+    assert np.array_equal(c.download_keys().astype(np.int64), keys) and M0 == len(co)
+    # window BA (fix clusters empty so far)
+    p1, tr1, _ = c.damping_iter(poses12_all[:N], gauge_mode=2, min_planes_per_pose=0)
+    # retire the two oldest scans
+    M1, K1 = c.marginalize(mg, p1, min_ps=15)
+    rp1, pi1, ob1, fx1, co1 = assoc_ref.marginalize_ref(N, rp, pi, ob, None, p1, mg, 15)
+    keep = _kept_mask(rp, pi, ob, mg, 15)
+    keys1 = keys[keep]
+    assert M1 == len(co1) and np.array_equal(c.download_keys().astype(np.int64), keys1)
+    # the window shifts: slots 0..N-mg-1 hold the remaining scans, the two new scans take slots N-mg and N-mg+1
+    shifted = np.vstack([p1[mg:], poses12_all[N:N + mg]])
+    kcur, rcur, picur, obcur, fxcur, cocur = keys1, rp1, pi1, ob1, fx1, co1
+    for j in range(mg):
+        slot = N - mg + j
+        new = pts[frs == N + j]
+        M2, K2, matched = c.append_scan(new.astype(np.float32), shifted, slot)
+        kcur, rcur, picur, obcur, fxcur, cocur, matched_ref = assoc_ref.append_scan_ref(
+            kcur, rcur, picur, obcur, fxcur, cocur, new, shifted, slot, **kw)
+        assert matched == matched_ref and matched > 0.3 * len(new)
+        assert M2 == len(cocur) and K2 == len(picur)
+        assert np.array_equal(c.download_keys().astype(np.int64), kcur)
+        rp_g, pi_g, ob_g, co_g = c.download_voxels()
+        assert np.array_equal(rp_g, rcur) and np.array_equal(pi_g, picur) and np.array_equal(co_g, cocur)
+        assert np.all(np.abs(ob_g - obcur) <= 1e-11 * np.abs(obcur).max(axis=0))
+        assert np.abs(c.download_fix() - fxcur).max() <= 1e-12 * np.abs(fxcur).max()
+        assert (pi_g == slot).sum() > 20                                  # the new scan really joined many voxels
+    # the window is full again: the next BA runs on it (the fix clusters carry the retired scans' information)
+    p2, tr2, _ = c.damping_iter(shifted, gauge_mode=2, min_planes_per_pose=0, hess_includes_fix=True)
+    assert np.isfinite(tr2[-1]["r2"]) and tr2[-1]["r2"] <= tr2[0]["r1"]
+    o = orc.Oracle(N, rcur, picur, obcur, cocur, fxcur)
+    st, p2o, tr2o, _ = o.damping_iter(shifted, gauge_mode=2, min_planes_per_pose=0, hess_includes_fix=True)
+    assert [t["accepted"] for t in tr2] == [t["accepted"] for t in tr2o]
+    assert np.abs(p2 - p2o).max() <= 1e-6
+
+
+def _kept_mask(row_ptr, pose_idx, obs10, mg, min_ps):
+    keep = []
+    for a in range(len(row_ptr) - 1):
+        ss = [s for s in range(row_ptr[a], row_ptr[a + 1]) if pose_idx[s] >= mg]
+        keep.append(len(ss) >= 2 and int(sum(obs10[s][9] for s in ss)) >= min_ps)
+    return np.array(keep, dtype=bool)
