@@ -92,7 +92,7 @@ def lib():
         L.balm_download_fix.argtypes = [C.c_void_p, C.c_void_p]
         L.balm_append_scan.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-        L.balm_download_keys.argtypes = [C.c_void_p, C.c_void_p]
+        L.balm_download_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -136,10 +136,11 @@ class Context:
         self.M = M.value
         return M.value, K.value, m.value
 
-    def download_keys(self):
+    def download_keys(self, with_layers=False):
         keys = np.zeros(self.M, dtype=np.uint64)
-        L.check(L.lib().balm_download_keys(self._h, _p(keys)))
-        return keys
+        layers = np.zeros(self.M, dtype=np.int32)
+        L.check(L.lib().balm_download_keys(self._h, _p(keys), _p(layers)))
+        return (keys, layers) if with_layers else keys
 
     def download_fix(self):
         fix = np.zeros((self.M, 10))

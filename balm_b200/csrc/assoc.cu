@@ -209,6 +209,10 @@ __global__ void leaf_count_kernel(const int *ref, int nleaf, const int *nf0, con
   const int L = ref[i] >> 28, v = ref[i] & 0x0FFFFFFF;
   cnt[i] = (L == 0 ? nf0 : (L == 1 ? nf1 : nf2))[v];
 }
+__global__ void leaf_layer_kernel(const int *ref, int nleaf, int *layer) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nleaf) layer[i] = ref[i] >> 28;
+}
 struct EmitLevel {
   const double *segB;
   const int *seg_frame, *node_start, *node_size;
@@ -409,6 +413,11 @@ int assoc_build(balm_ctx *c, int64_t n, const float *xyz_h, const int *frame_h, 
   c->vox_key = nullptr;
   CUDA_TRY(cudaMalloc((void **)&c->vox_key, sizeof(unsigned long long) * (size_t)nleaf));
   CUDA_TRY(cudaMemcpy(c->vox_key, lkey2, sizeof(unsigned long long) * (size_t)nleaf, cudaMemcpyDeviceToDevice));
+  cudaFree(c->vox_layer);
+  c->vox_layer = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&c->vox_layer, sizeof(int) * (size_t)nleaf));
+  leaf_layer_kernel<<<(unsigned)((nleaf + 127) / 128), 128, 0, st>>>(lref2, nleaf, c->vox_layer);
+  CUDA_TRY(cudaStreamSynchronize(st));
   c->has_keys = true;
   c->assoc_voxel_size = voxel_size; c->assoc_layer_limit = layer_limit; c->assoc_min_ps = min_ps;
   for (int q = 0; q < 3; q++) c->assoc_eig[q] = eig3[q];
@@ -518,12 +527,13 @@ __global__ void marg_emit_kernel(const long long *row_ptr, const int *pose_idx, 
                                  const double *fix /*SoA [10][M] or null*/, int64_t M, const double *poses, int mg,
                                  const int *keep, const int *vscan, const int *oscan, long long *row_ptr_out,
                                  int *pose_idx_out, double *obs10_out, double *fix10_out, double *coe_out, int64_t Mout,
-                                 int64_t Kout, const unsigned long long *key_in, unsigned long long *key_out) {
+                                 int64_t Kout, const unsigned long long *key_in, unsigned long long *key_out,
+                                 const int *layer_in, int *layer_out) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v == 0) row_ptr_out[Mout] = Kout;
   if (v >= M || !keep[v]) return;
   const int nv = vscan[v];
-  if (key_in) key_out[nv] = key_in[v];
+  if (key_in) { key_out[nv] = key_in[v]; layer_out[nv] = layer_in[v]; }
   long long o = oscan[v];
   row_ptr_out[nv] = o;
   double f[10];
@@ -555,13 +565,17 @@ __global__ void marg_emit_kernel(const long long *row_ptr, const int *pose_idx, 
 }  // namespace
 
 // after a re-registration: the compacted keys of the new voxel set (or none)
-static int install_keys(balm_ctx *c, const unsigned long long *keys_dev, int64_t M, bool have) {
+static int install_keys(balm_ctx *c, const unsigned long long *keys_dev, const int *layers_dev, int64_t M, bool have) {
   cudaFree(c->vox_key);
+  cudaFree(c->vox_layer);
   c->vox_key = nullptr;
+  c->vox_layer = nullptr;
   c->has_keys = false;
   if (!have) return BALM_OK;
   CUDA_TRY(cudaMalloc((void **)&c->vox_key, sizeof(unsigned long long) * (size_t)M));
+  CUDA_TRY(cudaMalloc((void **)&c->vox_layer, sizeof(int) * (size_t)M));
   CUDA_TRY(cudaMemcpy(c->vox_key, keys_dev, sizeof(unsigned long long) * (size_t)M, cudaMemcpyDeviceToDevice));
+  CUDA_TRY(cudaMemcpy(c->vox_layer, layers_dev, sizeof(int) * (size_t)M, cudaMemcpyDeviceToDevice));
   c->has_keys = true;
   return BALM_OK;
 }
@@ -597,17 +611,19 @@ int marginalize_build(balm_ctx *c, int mg, const double *poses_dev, int min_ps, 
   ATRY(pool.get(&rp, (size_t)Mout + 1)); ATRY(pool.get(&pi, (size_t)Kout)); ATRY(pool.get(&ob, (size_t)Kout * 10));
   ATRY(pool.get(&fx, (size_t)Mout * 10)); ATRY(pool.get(&co, (size_t)Mout));
   unsigned long long *keys_out = nullptr;
+  int *layers_out = nullptr;
   const bool had_keys = c->has_keys && c->vox_key;
-  if (had_keys) ATRY(pool.get(&keys_out, (size_t)Mout));
+  if (had_keys) { ATRY(pool.get(&keys_out, (size_t)Mout)); ATRY(pool.get(&layers_out, (size_t)Mout)); }
   marg_emit_kernel<<<gb, 128, 0, st>>>(c->row_ptr, c->pose_idx, c->obs, c->Kp, c->fix, M, poses_dev, mg, keep, vscan, oscan, rp,
-                                       pi, ob, fx, co, Mout, Kout, had_keys ? c->vox_key : nullptr, keys_out);
+                                       pi, ob, fx, co, Mout, Kout, had_keys ? c->vox_key : nullptr, keys_out, c->vox_layer,
+                                       layers_out);
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   c->launches += 4;
   if (Mout < 1) { balm_set_error("balm_marginalize: no voxel is left with two observing scans"); return BALM_ERR_INVALID; }
   // re-register from the device arrays (copies them, transposes the observations, rebuilds the pose-major lists)
   ATRY(reg(c, Mout, (const int64_t *)rp, pi, ob, fx, co, Kout));
-  return install_keys(c, keys_out, Mout, had_keys);
+  return install_keys(c, keys_out, layers_out, Mout, had_keys);
 }
 
 
@@ -624,7 +640,8 @@ int marginalize_build(balm_ctx *c, int mg, const double *poses_dev, int min_ps, 
 // -- both appear at the next full balm_cut_voxels.
 namespace {
 __global__ void append_match_kernel(const float *xyz, const double *pose12, int64_t n, AssocParams p,
-                                    const unsigned long long *vox_key, int M, unsigned *vid1, int *bad) {
+                                    const unsigned long long *vox_key, const int *vox_layer, int M, unsigned *vid1,
+                                    int *bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double r[9], t[3];
@@ -636,9 +653,11 @@ __global__ void append_match_kernel(const float *xyz, const double *pose12, int6
   int dummy = 0;
   (void)bad;
   const unsigned long long k = world_point_key(w, p, &dummy);
+  // a key digit 7 means "not split" AND is octant 7, so a hit only counts when the voxel's layer agrees
   int v = find_key(vox_key, M, k | 63ull);            // a layer-0 leaf (the whole root voxel is one plane)
-  if (v < 0) v = find_key(vox_key, M, k | 7ull);      // a layer-1 leaf
-  if (v < 0) v = find_key(vox_key, M, k);             // a layer-2 leaf
+  if (v >= 0 && vox_layer[v] != 0) v = -1;
+  if (v < 0) { v = find_key(vox_key, M, k | 7ull); if (v >= 0 && vox_layer[v] != 1) v = -1; }   // a layer-1 leaf
+  if (v < 0) { v = find_key(vox_key, M, k); if (v >= 0 && vox_layer[v] != 2) v = -1; }          // a layer-2 leaf
   vid1[i] = (unsigned)(v + 1);                        // 0 = the point falls into no registered plane voxel
 }
 // one thread per voxel: the new scan's body-frame cluster (points in their original order)
@@ -662,7 +681,7 @@ __global__ void append_cluster_kernel(const float *xyz, const unsigned *vid_sort
 // one thread per voxel: judge_eigen on fix + every window cluster (old ones and the new one) at the current poses
 __global__ void append_judge_kernel(const long long *row_ptr, const int *pose_idx, const double *obs, int64_t Kp,
                                     const double *fix, int64_t M, const double *poses, const double *newobs, int slot,
-                                    const unsigned long long *vox_key, AssocParams p, int *keep, int *cnt, int *bad) {
+                                    const int *vox_layer, AssocParams p, int *keep, int *cnt, int *bad) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= M) return;
   double W[10];
@@ -696,8 +715,7 @@ __global__ void append_judge_kernel(const long long *row_ptr, const int *pose_id
   double lam[3], u0[3], u1[3], u2[3];
   eig3_jacobi(W[0] * inv - c0 * c0, W[1] * inv - c0 * c1, W[2] * inv - c0 * c2, W[3] * inv - c1 * c1,
               W[4] * inv - c1 * c2, W[5] * inv - c2 * c2, lam, u0, u1, u2);
-  const unsigned long long key = vox_key[v];
-  const int layer = (key & 63ull) == 63ull ? 0 : ((key & 7ull) == 7ull ? 1 : 2);
+  const int layer = vox_layer[v];
   const bool planar = lam[0] / lam[1] < p.eig[layer];                     // judge_eigen (:665,697)
   const int kp = (planar && (int)pts > p.min_ps && k >= 2) ? 1 : 0;       // recut :755-757, push_voxel :37
   keep[v] = kp;
@@ -706,8 +724,9 @@ __global__ void append_judge_kernel(const long long *row_ptr, const int *pose_id
 __global__ void append_emit_kernel(const long long *row_ptr, const int *pose_idx, const double *obs, int64_t Kp,
                                    const double *fix, const double *coe, int64_t M, const double *newobs, int slot,
                                    const int *keep, const int *vscan, const int *oscan, const unsigned long long *key_in,
-                                   long long *row_ptr_out, int *pose_idx_out, double *obs10_out, double *fix10_out,
-                                   double *coe_out, unsigned long long *key_out, int64_t Mout, int64_t Kout) {
+                                   const int *layer_in, long long *row_ptr_out, int *pose_idx_out, double *obs10_out,
+                                   double *fix10_out, double *coe_out, unsigned long long *key_out, int *layer_out,
+                                   int64_t Mout, int64_t Kout) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v == 0) row_ptr_out[Mout] = Kout;
   if (v >= M || !keep[v]) return;
@@ -715,6 +734,7 @@ __global__ void append_emit_kernel(const long long *row_ptr, const int *pose_idx
   long long o = oscan[v];
   row_ptr_out[nv] = o;
   key_out[nv] = key_in[v];
+  layer_out[nv] = layer_in[v];
   for (long long s = row_ptr[v]; s < row_ptr[v + 1]; s++, o++) {
     for (int q = 0; q < 10; q++) obs10_out[o * 10 + q] = obs[q * Kp + s];
     pose_idx_out[o] = pose_idx[s];
@@ -748,7 +768,7 @@ int append_scan_build(balm_ctx *c, int64_t n, const float *xyz_h, const double *
   CUDA_TRY(cudaMemcpyAsync(xyz, xyz_h, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int), st));
   const unsigned gp = (unsigned)((n + 255) / 256), gv = (unsigned)((M + 127) / 128);
-  append_match_kernel<<<gp, 256, 0, st>>>(xyz, poses_dev + 12 * slot, n, P, c->vox_key, (int)M, vid, bad);
+  append_match_kernel<<<gp, 256, 0, st>>>(xyz, poses_dev + 12 * slot, n, P, c->vox_key, c->vox_layer, (int)M, vid, bad);
   iota_kernel<<<gp, 256, 0, st>>>(idx, n);
   int bits = 1;
   while ((1ll << bits) <= M) bits++;
@@ -760,7 +780,7 @@ int append_scan_build(balm_ctx *c, int64_t n, const float *xyz_h, const double *
   ATRY(pool.get(&tmp, tb));
   CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, vid, vid2, idx, idx2, (int)n, 0, bits, st));  // stable: point order kept
   append_cluster_kernel<<<gv, 128, 0, st>>>(xyz, vid2, idx2, n, (int)M, newobs);
-  append_judge_kernel<<<gv, 128, 0, st>>>(c->row_ptr, c->pose_idx, c->obs, c->Kp, c->fix, M, poses_dev, newobs, slot, c->vox_key, P,
+  append_judge_kernel<<<gv, 128, 0, st>>>(c->row_ptr, c->pose_idx, c->obs, c->Kp, c->fix, M, poses_dev, newobs, slot, c->vox_layer, P,
                                           keep, cnt, bad);
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tb, keep, vscan, (int)M, st));
   CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, oscan, (int)M, st));
@@ -783,10 +803,12 @@ int append_scan_build(balm_ctx *c, int64_t n, const float *xyz_h, const double *
   int *pi = nullptr;
   double *ob = nullptr, *fx = nullptr, *co = nullptr;
   unsigned long long *keys_out = nullptr;
+  int *layers_out = nullptr;
   ATRY(pool.get(&rp, (size_t)Mout + 1)); ATRY(pool.get(&pi, (size_t)Kout)); ATRY(pool.get(&ob, (size_t)Kout * 10));
   ATRY(pool.get(&fx, (size_t)Mout * 10)); ATRY(pool.get(&co, (size_t)Mout)); ATRY(pool.get(&keys_out, (size_t)Mout));
+  ATRY(pool.get(&layers_out, (size_t)Mout));
   append_emit_kernel<<<gv, 128, 0, st>>>(c->row_ptr, c->pose_idx, c->obs, c->Kp, c->fix, c->coe, M, newobs, slot, keep, vscan, oscan,
-                                         c->vox_key, rp, pi, ob, fx, co, keys_out, Mout, Kout);
+                                         c->vox_key, c->vox_layer, rp, pi, ob, fx, co, keys_out, layers_out, Mout, Kout);
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
   c->launches += 8;
@@ -794,5 +816,5 @@ int append_scan_build(balm_ctx *c, int64_t n, const float *xyz_h, const double *
   *K_out = Kout;
   const bool any_fix = c->fix != nullptr;
   ATRY(reg(c, Mout, (const int64_t *)rp, pi, ob, any_fix ? fx : nullptr, co, Kout));
-  return install_keys(c, keys_out, Mout, true);
+  return install_keys(c, keys_out, layers_out, Mout, true);
 }

@@ -73,7 +73,9 @@ static void free_problem(balm_ctx *c) {
 }
 static void drop_keys(balm_ctx *c) {  // a voxel set registered from arrays carries no octree keys
   cudaFree(c->vox_key);
+  cudaFree(c->vox_layer);
   c->vox_key = nullptr;
+  c->vox_layer = nullptr;
   c->has_keys = false;
 }
 
@@ -215,7 +217,7 @@ extern "C" int balm_destroy(balm_ctx *c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaFree(c->poses); cudaFree(c->poses_trial); cudaFree(c->H); cudaFree(c->A); cudaFree(c->W);
   cudaFree(c->dx); cudaFree(c->dvec); cudaFree(c->scal); cudaFree(c->flags); cudaFree(c->accum); cudaFree(c->accum_batch);
-  cudaFree(c->vox_key); cudaFree(c->res_part); cudaFree(c->planes); cudaFree(c->Xinv); cudaFree(c->dinv); cudaFree(c->sol); cudaFree(c->ysol);
+  cudaFree(c->vox_key); cudaFree(c->vox_layer); cudaFree(c->res_part); cudaFree(c->planes); cudaFree(c->Xinv); cudaFree(c->dinv); cudaFree(c->sol); cudaFree(c->ysol);
   cudaFree(c->Hpack); cudaFree(c->dval); cudaFree(c->rres); cudaFree(c->rdelta); cudaFree(c->dag_flags);
   if (c->solve_graph) cudaGraphExecDestroy((cudaGraphExec_t)c->solve_graph);
   cudaFreeHost(c->h_scal); cudaFreeHost(c->h_flags);
@@ -856,10 +858,11 @@ extern "C" int balm_append_scan(balm_ctx *c, int64_t n_points, const float *xyz,
   if (n_obs_out) *n_obs_out = K;
   return BALM_OK;
 }
-extern "C" int balm_download_keys(balm_ctx *c, uint64_t *keys) {
-  if (!c || !keys || !c->has_keys) { balm_set_error("balm_download_keys: the voxel set carries no octree keys"); return BALM_ERR_INVALID; }
+extern "C" int balm_download_keys(balm_ctx *c, uint64_t *keys, int32_t *layers) {
+  if (!c || !c->has_keys) { balm_set_error("balm_download_keys: the voxel set carries no octree keys"); return BALM_ERR_INVALID; }
   CUDA_TRY(cudaSetDevice(c->device));
-  CUDA_TRY(cudaMemcpy(keys, c->vox_key, sizeof(uint64_t) * (size_t)c->M, cudaMemcpyDeviceToHost));
+  if (keys) CUDA_TRY(cudaMemcpy(keys, c->vox_key, sizeof(uint64_t) * (size_t)c->M, cudaMemcpyDeviceToHost));
+  if (layers) CUDA_TRY(cudaMemcpy(layers, c->vox_layer, sizeof(int32_t) * (size_t)c->M, cudaMemcpyDeviceToHost));
   return BALM_OK;
 }
 extern "C" int balm_download_fix(balm_ctx *c, double *fix10) {

@@ -59,6 +59,8 @@ struct balm_ctx {
   bool registered = false;        // a voxel set (possibly empty: a rank whose shard has no voxels) is registered
   unsigned long long *vox_key = nullptr;  // [M] 63-bit octree key of every voxel (ascending) when the set came from
                                           // balm_cut_voxels: lets balm_append_scan find the leaf a new point falls into
+  int *vox_layer = nullptr;       // [M] octree layer of every voxel (a key digit 7 is BOTH octant 7 and "not split":
+                                  // the layer says which)
   bool has_keys = false;
   double assoc_voxel_size = 1.0;  // association parameters of that call
   int assoc_layer_limit = 2, assoc_min_ps = 15;

@@ -235,7 +235,8 @@ def cpu_baseline_once(n_poses, voxels_total, m_small, m_large):
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path. The reference needs Eigen, PCL and ROS,
-    none of which exist in this image (no baseline/_ref, no oracle/_ref), so the arm times the oracle port of the
+    none of which exist in this image (no baseline/_ref; oracle/_ref holds the reference's headers compiled against
+    stand-in Eigen, a correctness pin whose speed says nothing about Eigen's), so the arm times the oracle port of the
     reference loop nest (CpuArm). A step = one bounded sample of an LM iteration (both sample sizes + the full-size
     solve); `ms_per_step` is that measured time, `value` the throughput EXTRAPOLATED to the full workload from it.
     No balm_b200 code runs."""

@@ -156,10 +156,11 @@ int balm_download_fix(balm_ctx *ctx, double *fix10);
  * kept with coe = window points; otherwise dropped. Not done here (it happens at the next full balm_cut_voxels): new
  * roots / leaves from points outside the registered planes, re-splitting a leaf that stopped being planar.
  * n_matched_out: points that fell into a registered voxel. balm_download_keys copies the M voxel keys
- * ([root x|y|z biased by 2^18, 19 bits each | octant at layer 1 | octant at layer 2], 7 = not split). */
+ * ([root x|y|z biased by 2^18, 19 bits each | octant at layer 1 | octant at layer 2], 7 = not split) and their octree
+ * layers (0..2; a digit 7 is also octant 7, the layer tells the two apart); either pointer may be NULL. */
 int balm_append_scan(balm_ctx *ctx, int64_t n_points, const float *xyz, const double *poses12, int slot,
                      int64_t *n_voxels_out, int64_t *n_obs_out, int64_t *n_matched_out);
-int balm_download_keys(balm_ctx *ctx, uint64_t *keys);
+int balm_download_keys(balm_ctx *ctx, uint64_t *keys, int32_t *layers);
 
 /* Pose-covariance propagation of the consistency experiment:
  *   Rcov_raw = sum over observations of  Ls c_cov Ls^T      -- VOX_HESS::left_jacobian_point + BALM2::multi_second

@@ -1,6 +1,6 @@
 /*
  * balm_oracle.c -- CPU restatement of the BALM 2.0 BA hot path.  TEST INFRASTRUCTURE ONLY
- * (see balm_oracle.h for the scope, the reference file:line map and the "parity unpinned" note).
+ * (see balm_oracle.h for the scope, the reference file:line map and the parity-pin note).
  *
  * Written for fidelity to the reference loop nest, not for speed: the O(k^2) 6x6 pair loop with
  * read-modify-write into a dense column-major n x n matrix (bavoxel.hpp:404-418), the upper->lower

@@ -13,11 +13,16 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (libbalm_b200.so) never links or calls it.
  *
- * PARITY UNPINNED: the reference has no tests, golden vectors or fixed seeds, and its
- * only third-party arithmetic -- Eigen (unpinned; "3.3.7 recommended", README.md:29):
- * SelfAdjointEigenSolver<Matrix3d> (bavoxel.hpp:345,452) and MatrixXd::ldlt() (bavoxel.hpp:1114) -- is
- * absent from this image, so the reference itself cannot be compiled here.  The oracle is instead pinned by
- * analytic identities and finite differences (tests/test_oracle.py) and by an independent numpy restatement.
+ * PARITY PIN: the reference has no tests, golden vectors or fixed seeds, and Eigen / PCL / ROS are
+ * absent from this image, so the reference cannot be built as shipped.  Its OWN headers do compile, verbatim and where they
+ * lie, against stand-ins for the few Eigen / PCL / ROS names they use (oracle/ref_stubs/, oracle/ref_harness*.cpp ->
+ * oracle/_ref/libbalm_ref*.so, recipe in oracle/Makefile): tests/test_reference_pin.py checks this oracle and the numpy
+ * restatements against that code (Exp/Log, left_evaluate_acc2, evaluate_only_residual, divide_thread_left, the solve line,
+ * damping_iter end to end, cut_voxel/recut/tras_opt, marginalize, the simulation's left_jacobian_point / covariance push).
+ * STILL UNPINNED: Eigen's own arithmetic -- SelfAdjointEigenSolver<Matrix3d> (bavoxel.hpp:345,452) and MatrixXd::ldlt()
+ * (bavoxel.hpp:1114); version unpinned, "3.3.7 recommended", README.md:29 -- is a stand-in there too; H, g, r are invariant
+ * to the eigenvector sign and the solve is checked by its residual, and that boundary is covered by analytic identities,
+ * finite differences and an independent numpy restatement (tests/test_oracle.py).
  *
  * Data layout (shared with include/balm_b200.h):
  *   poses12 : N x 12 doubles, per pose R column-major (R00,R10,R20,R01,...,R22) then p (3)   [IMUST R,p]

@@ -30,8 +30,10 @@ def node_key(root, o1, o2):
     return (((int(root[0]) + b) << 44) | ((int(root[1]) + b) << 25) | ((int(root[2]) + b) << 6) | (o1 << 3) | o2)
 
 
-def cut_voxels(points_body, frames, poses, **kw):
-    """points_body: n x 3 float64 (already rounded to the float32 the PCD stores), frames: n int, poses: list of (R, p)."""
+def cut_voxels(points_body, frames, poses, with_layers=False, **kw):
+    """points_body: n x 3 float64 (already rounded to the float32 the PCD stores), frames: n int, poses: list of (R, p).
+    with_layers: also return every leaf's octree layer -- a key digit 7 is both "not split" and octant 7, so the layer
+    cannot be read back from the key."""
     o = dict(DEFAULTS)
     o.update(kw)
     vs, lim, min_ps = o["voxel_size"], o["layer_limit"], o["min_ps"]
@@ -53,7 +55,7 @@ def cut_voxels(points_body, frames, poses, **kw):
         cov = pw_.T @ pw_ / n - np.outer(c, c)
         lam = np.linalg.eigvalsh(cov)
         if lam[0] / lam[1] < float(np.float32(o["eigen_value_array"][layer])):  # `float eigen_value_array[]`, bavoxel.hpp:11
-            leaves.append((node_key(root, path[0], path[1]), pb_, fr_))
+            leaves.append((node_key(root, path[0], path[1]), pb_, fr_, layer))
             return
         if layer == lim:
             return
@@ -72,8 +74,8 @@ def cut_voxels(points_body, frames, poses, **kw):
         center = ((0.5 + key[a]) * vs).astype(np.float32).astype(np.float64)
         recut(pb[a:b], pw[a:b], fr[a:b], center, vs / 4.0, 0, key[a], (7, 7))
     leaves.sort(key=lambda x: x[0])
-    row_ptr, pose_idx, obs, coe, keys = [0], [], [], [], []
-    for k, q, f in leaves:
+    row_ptr, pose_idx, obs, coe, keys, layers = [0], [], [], [], [], []
+    for k, q, f, lay in leaves:
         fs = np.unique(f)
         if len(q) < min_ps or len(fs) < 2:
             continue
@@ -86,8 +88,10 @@ def cut_voxels(points_body, frames, poses, **kw):
         row_ptr.append(len(pose_idx))
         coe.append(float(len(q)))
         keys.append(k)
-    return (np.array(row_ptr, dtype=np.int64), np.array(pose_idx, dtype=np.int32), np.array(obs, dtype=np.float64),
-            np.array(coe, dtype=np.float64), np.array(keys, dtype=np.int64))
+        layers.append(lay)
+    out = (np.array(row_ptr, dtype=np.int64), np.array(pose_idx, dtype=np.int32), np.array(obs, dtype=np.float64),
+           np.array(coe, dtype=np.float64), np.array(keys, dtype=np.int64))
+    return out + (np.array(layers, dtype=np.int32),) if with_layers else out
 
 
 def synthetic_scans(n_poses=12, pts_per_scan=6000, seed=5, room=6.0):
@@ -175,12 +179,15 @@ def point_keys(world, voxel_size):
     return root, 4 * b1[:, 0] + 2 * b1[:, 1] + b1[:, 2], 4 * b2[:, 0] + 2 * b2[:, 1] + b2[:, 2]
 
 
-def append_scan_ref(keys, row_ptr, pose_idx, obs10, fix10, coe, points_body, poses12, slot, **kw):
+def append_scan_ref(keys, layers, row_ptr, pose_idx, obs10, fix10, coe, points_body, poses12, slot, **kw):
     """numpy restatement of balm_append_scan: the new scan's points find their plane leaf (cut_voxel + cut_func), their
     body-frame moments become the leaf's observation in pose slot `slot`, and every leaf is re-judged as recut does
     (bavoxel.hpp:737-776 -> judge_eigen :654-699): fix_point + all window clusters transformed by the current poses must be
     planar (eigen ratio below the layer's threshold), hold more than min_ps window points and be seen by >= 2 scans.
-    -> keys, row_ptr, pose_idx, obs10, fix10, coe of the leaves that are pushed again, and the number of matched points."""
+    A point descends root -> octant -> octant and stops at the first plane leaf on its path (cut_func :700-735): a leaf
+    only matches at its own layer (`layers`; the key digit 7 alone is ambiguous with octant 7).
+    -> keys, layers, row_ptr, pose_idx, obs10, fix10, coe of the leaves that are pushed again, and the number of matched
+    points."""
     o = dict(DEFAULTS)
     o.update(kw)
     vs, min_ps = o["voxel_size"], o["min_ps"]
@@ -192,13 +199,14 @@ def append_scan_ref(keys, row_ptr, pose_idx, obs10, fix10, coe, points_body, pos
     new_pts = {}
     matched = 0
     for i in range(len(points_body)):
-        for cand in (node_key(root[i], 7, 7), node_key(root[i], int(o1[i]), 7), node_key(root[i], int(o1[i]), int(o2[i]))):
+        for lay, cand in enumerate((node_key(root[i], 7, 7), node_key(root[i], int(o1[i]), 7),
+                                    node_key(root[i], int(o1[i]), int(o2[i])))):
             a = keymap.get(cand)
-            if a is not None:
+            if a is not None and int(layers[a]) == lay:
                 new_pts.setdefault(a, []).append(points_body[i])
                 matched += 1
                 break
-    out_k, rp, pi, ob, fx, co = [], [0], [], [], [], []
+    out_k, out_l, rp, pi, ob, fx, co = [], [], [0], [], [], [], []
     for a, k in enumerate(keys):
         rows = [(int(pose_idx[s]), np.array(obs10[s], dtype=np.float64)) for s in range(row_ptr[a], row_ptr[a + 1])]
         if a in new_pts:
@@ -219,7 +227,7 @@ def append_scan_ref(keys, row_ptr, pose_idx, obs10, fix10, coe, points_body, pos
         cen = W[6:9] / W[9]
         cov = np.array([[W[0], W[1], W[2]], [W[1], W[3], W[4]], [W[2], W[4], W[5]]]) / W[9] - np.outer(cen, cen)
         lam = np.linalg.eigvalsh(cov)
-        layer = 0 if (int(k) & 63) == 63 else (1 if (int(k) & 7) == 7 else 2)
+        layer = int(layers[a])
         pts = sum(c[9] for _, c in rows)
         if not (lam[0] / lam[1] < float(np.float32(o["eigen_value_array"][layer]))) or int(pts) <= min_ps or len(rows) < 2:
             continue
@@ -228,7 +236,9 @@ def append_scan_ref(keys, row_ptr, pose_idx, obs10, fix10, coe, points_body, pos
             ob.append(c)
         rp.append(len(pi))
         out_k.append(int(k))
+        out_l.append(layer)
         fx.append(fix)
         co.append(float(pts))
-    return (np.array(out_k, dtype=np.int64), np.array(rp, dtype=np.int64), np.array(pi, dtype=np.int32),
+    return (np.array(out_k, dtype=np.int64), np.array(out_l, dtype=np.int32), np.array(rp, dtype=np.int64),
+            np.array(pi, dtype=np.int32),
             np.array(ob).reshape(-1, 10), np.array(fx).reshape(-1, 10), np.array(co), matched)

@@ -52,28 +52,33 @@ def test_sliding_window_on_the_device_matches_the_restatement():
     c = balm_b200.Context(N, 0, 0)
     kw = dict(voxel_size=2.0, layer_limit=2, min_ps=15, eigen_value_array=(1 / 16, 1 / 16, 1 / 16))
     M0, K0 = c.cut_voxels(pts[win].astype(np.float32), frs[win], poses12_all[:N], **kw)
-    rp, pi, ob, co, keys = assoc_ref.cut_voxels(pts[win], frs[win], poses[:N], **kw)
-    assert np.array_equal(c.download_keys().astype(np.int64), keys) and M0 == len(co)
+    rp, pi, ob, co, keys, lays = assoc_ref.cut_voxels(pts[win], frs[win], poses[:N], with_layers=True, **kw)
+    kg, lg = c.download_keys(with_layers=True)
+    assert np.array_equal(kg.astype(np.int64), keys) and np.array_equal(lg, lays) and M0 == len(co)
+    # the case the layers exist for: a layer-1 leaf in octant 7 carries the same key digits as a layer-0 / layer-2 pattern
+    assert ((keys & 63) == 63).sum() > (lays == 0).sum() or ((keys & 7) == 7).sum() > (lays <= 1).sum()
     # window BA (fix clusters empty so far)
     p1, tr1, _ = c.damping_iter(poses12_all[:N], gauge_mode=2, min_planes_per_pose=0)
     # retire the two oldest scans
     M1, K1 = c.marginalize(mg, p1, min_ps=15)
     rp1, pi1, ob1, fx1, co1 = assoc_ref.marginalize_ref(N, rp, pi, ob, None, p1, mg, 15)
     keep = _kept_mask(rp, pi, ob, mg, 15)
-    keys1 = keys[keep]
-    assert M1 == len(co1) and np.array_equal(c.download_keys().astype(np.int64), keys1)
+    keys1, lays1 = keys[keep], lays[keep]
+    kg, lg = c.download_keys(with_layers=True)
+    assert M1 == len(co1) and np.array_equal(kg.astype(np.int64), keys1) and np.array_equal(lg, lays1)
     # the window shifts: slots 0..N-mg-1 hold the remaining scans, the two new scans take slots N-mg and N-mg+1
     shifted = np.vstack([p1[mg:], poses12_all[N:N + mg]])
-    kcur, rcur, picur, obcur, fxcur, cocur = keys1, rp1, pi1, ob1, fx1, co1
+    kcur, lcur, rcur, picur, obcur, fxcur, cocur = keys1, lays1, rp1, pi1, ob1, fx1, co1
     for j in range(mg):
         slot = N - mg + j
         new = pts[frs == N + j]
         M2, K2, matched = c.append_scan(new.astype(np.float32), shifted, slot)
-        kcur, rcur, picur, obcur, fxcur, cocur, matched_ref = assoc_ref.append_scan_ref(
-            kcur, rcur, picur, obcur, fxcur, cocur, new, shifted, slot, **kw)
+        kcur, lcur, rcur, picur, obcur, fxcur, cocur, matched_ref = assoc_ref.append_scan_ref(
+            kcur, lcur, rcur, picur, obcur, fxcur, cocur, new, shifted, slot, **kw)
         assert matched == matched_ref and matched > 0.3 * len(new)
         assert M2 == len(cocur) and K2 == len(picur)
-        assert np.array_equal(c.download_keys().astype(np.int64), kcur)
+        kg, lg = c.download_keys(with_layers=True)
+        assert np.array_equal(kg.astype(np.int64), kcur) and np.array_equal(lg, lcur)
         rp_g, pi_g, ob_g, co_g = c.download_voxels()
         assert np.array_equal(rp_g, rcur) and np.array_equal(pi_g, picur) and np.array_equal(co_g, cocur)
         assert np.all(np.abs(ob_g - obcur) <= 1e-11 * np.abs(obcur).max(axis=0))
