@@ -966,6 +966,13 @@ extern "C" int balm_debug_dag_trace(balm_ctx *c, unsigned long long *out, int ma
   return BALM_OK;
 }
 
+int tensor_overlap_probe(balm_ctx *c, const double *poses, int reps, float *out);
+extern "C" int balm_debug_overlap_probe(balm_ctx *c, int reps, float *out5) {
+  if (!c || !out5 || c->prec != BALM_PREC_TENSOR) return BALM_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(c->device));
+  return tensor_overlap_probe(c, c->poses, reps, out5);
+}
+
 extern "C" int balm_device_views(balm_ctx *c, double **H_dev, double **g_dev) {
   if (!c) return BALM_ERR_INVALID;
   if (H_dev) *H_dev = c->H;

@@ -245,10 +245,10 @@ enum { OBS_FP64 = 0, OBS_MAXONLY = 1, OBS_INT8 = 2, OBS_FUSED = 3 };
 //                   step moves the column maxima by far less than the factor 2 of headroom a balanced top digit
 //                   has); tc_scale_kernel checks the new maxima against the scales used and, if a column overflowed
 //                   or lost precision, re-arms the OBS_INT8 sweep (which otherwise returns at once)
-template <bool DENSE, int MODE>
-__global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
+template <bool DENSE, int MODE, int WPC = 4>
+__global__ void __launch_bounds__(WPC * 32) obs_pass_kernel(ObsArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile = blockIdx.y * 4 + warp;
+  const int tile = blockIdx.y * WPC + warp;
   const int i = tile * 32 + lane;
   if (tile * 32 >= a.N) return;
   if (MODE == OBS_INT8 && a.skip && *a.skip) return;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(128) obs_pass_kernel(ObsArgs a) {
   // dense scenes: the voxel is warp-uniform, so its 20 stats words are fetched ONE ITERATION AHEAD by lanes 0..19
   // (one word each), parked in a per-warp shared-memory slot at the top of the iteration and read back as
   // broadcasts -- instead of ten L2-latency loads whose result is needed immediately
-  __shared__ __align__(16) double s_stats[4][2][BALM_STATS_STRIDE];
+  __shared__ __align__(16) double s_stats[WPC][2][BALM_STATS_STRIDE];
   double st_next = 0.0;
   if (DENSE && lane < BALM_STATS_STRIDE && t0 < t1) st_next = __ldg(a.stats + (t0 - a.v0) * BALM_STATS_STRIDE + lane);
   for (long long t = t0; t < t1; t++) {
@@ -587,7 +587,7 @@ int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, 
 // accumulators AND digit planes with the previous evaluation's scales); `skip`: device flag that disarms sweep 2.
 int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch, const double *sc,
                     int8_t *Gq, int64_t plane_stride, const int *S_dev, int S_alloc, int64_t rows_padded, bool fused,
-                    const int *skip) {
+                    const int *skip, int wpc) {
   const int64_t nv = v1 - v0;
   if (nv <= 0) return BALM_OK;
   ObsArgs a;
@@ -607,7 +607,10 @@ int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bo
     }
   }
   if (fused) {
-    if (c->dense) obs_pass_kernel<true, OBS_FUSED><<<grid, 128, 0, c->stream>>>(a);
+    if (c->dense && wpc == 3) {  // 96-thread CTAs: one of them fits next to a resident SYRK CTA (register file)
+      grid.y = ((c->N + 31) / 32 + 2) / 3;
+      obs_pass_kernel<true, OBS_FUSED, 3><<<grid, 96, 0, c->stream>>>(a);
+    } else if (c->dense) obs_pass_kernel<true, OBS_FUSED><<<grid, 128, 0, c->stream>>>(a);
     else obs_pass_kernel<false, OBS_FUSED><<<grid, 128, 0, c->stream>>>(a);
     const int total = BALM_ACC * c->Np;
     obs_reduce_kernel<<<(total + 255) / 256, 256, 0, c->stream>>>(c->obs_part, chunks, total, c->accum,

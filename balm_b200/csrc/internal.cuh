@@ -276,7 +276,7 @@ int launch_obs_pass(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bo
 int launch_obs_colmax(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_obs_int8(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch, const double *sc,
                     int8_t *Gq, int64_t plane_stride, const int *S_dev, int S_alloc, int64_t rows_padded, bool fused,
-                    const int *skip);
+                    const int *skip, int wpc = 4);
 int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1, bool first_batch);
 int launch_syrk_f64(balm_ctx *c, int64_t rows, bool first_batch);
 int launch_assemble(balm_ctx *c);

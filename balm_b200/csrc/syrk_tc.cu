@@ -541,8 +541,7 @@ __device__ __forceinline__ void mma_issue_loop_2sm(const TcArgs &a, uint8_t *sta
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-    syrk_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b64, TcArgs a) {
+__device__ __forceinline__ void syrk_tc_2sm_body(const CUtensorMap &tmap, const CUtensorMap &tmap_b64, const TcArgs &a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *stage_base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_base + RING_BYTES);
@@ -685,6 +684,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512));
   }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    syrk_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b64, TcArgs a) {
+  syrk_tc_2sm_body(tmap, tmap_b64, a);
+}
+// the same kernel inside 128 registers per thread (the bound of a 512-thread CTA): 320 x 128 = 40 960 registers leave room
+// for a 96-thread CTA of the observation sweep (248 registers) on the same SM
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
+    syrk_tc_2sm_r128_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b64, TcArgs a) {
+  syrk_tc_2sm_body(tmap, tmap_b64, a);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
@@ -941,6 +951,7 @@ int tensor_syrk_init(balm_ctx *c) {
   CUDA_TRY(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUDA_TRY(cudaFuncSetAttribute(syrk_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUDA_TRY(cudaFuncSetAttribute(syrk_tc_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(syrk_tc_2sm_r128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return BALM_OK;
 }
 
@@ -1021,6 +1032,71 @@ int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1
   }
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
+  return BALM_OK;
+}
+
+// Experiment (scripts/overlap_probe.py): can the observation sweep run NEXT TO the SYRK on the same SMs? Needs a
+// tensor-mode, dense, single-batch context whose last damping_iter left valid scales, stats and digit planes. Times
+//   out[0] the 2-SM SYRK alone (168 registers)          out[1] the same inside 128 registers
+//   out[2] the fused sweep alone with 128-thread CTAs   out[3] with 96-thread CTAs
+//   out[4] SYRK (128 registers, high-priority stream) and the 96-thread sweep launched together
+// The sweep rewrites the digit planes with the values they already hold (same poses, same scales).
+int tensor_overlap_probe(balm_ctx *c, const double *poses, int reps, float *out) {
+  TcState *st = static_cast<TcState *>(c->tmap);
+  if (!st || !st->use_2sm || !c->dense || c->VB < c->M || !st->spec_ready) {
+    balm_set_error("overlap probe: needs the 2-SM tensor path, a dense single-batch problem and a finished damping_iter");
+    return BALM_ERR_INVALID;
+  }
+  const int64_t rows = 3 * c->M, rows_padded = (rows + KS - 1) / KS * KS;
+  const int64_t plane_stride = (int64_t)st->rows_alloc * c->ldg;
+  TcArgs a{rows_padded, c->syrk_nb, c->syrk_tiles, c->syrk_splits, st->S_dev, st->isc, c->syrk_part,
+           0, st->err, 1, st->pairs2, st->n_pairs2};
+  const int smem = RING_BYTES + 1024 + 256;
+  const int items = a.n_pairs * a.splits;
+  int clusters = c->sm_count / 2;
+  if (items < clusters) clusters = items;
+  cudaStream_t hi;
+  int lo_p, hi_p;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+  CUDA_TRY(cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, hi_p));
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  auto syrk = [&](bool r128, cudaStream_t s) {
+    if (r128) syrk_tc_2sm_r128_kernel<<<2 * clusters, TC_THREADS, smem, s>>>(st->map, st->map_b64, a);
+    else syrk_tc_2sm_kernel<<<2 * clusters, TC_THREADS, smem, s>>>(st->map, st->map_b64, a);
+  };
+  auto sweep = [&](int wpc) {
+    return launch_obs_int8(c, poses, 0, c->M, true, st->sc, c->Gq, plane_stride, st->S_dev, SMAX, rows_padded, true, nullptr, wpc);
+  };
+  for (int mode = 0; mode < 5; mode++) {
+    float best = 1e30f;
+    for (int r = 0; r < reps + 1; r++) {
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      CUDA_TRY(cudaStreamSynchronize(hi));
+      CUDA_TRY(cudaEventRecord(e0, c->stream));
+      if (mode == 0) syrk(false, c->stream);
+      if (mode == 1) syrk(true, c->stream);
+      if (mode == 2) { int rc = sweep(4); if (rc) return rc; }
+      if (mode == 3) { int rc = sweep(3); if (rc) return rc; }
+      if (mode == 4) {
+        CUDA_TRY(cudaStreamWaitEvent(hi, e0, 0));
+        syrk(true, hi);
+        CUDA_TRY(cudaEventRecord(e2, hi));
+        int rc = sweep(3);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, e2, 0));
+      }
+      CUDA_TRY(cudaEventRecord(e1, c->stream));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      CUDA_TRY(cudaGetLastError());
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (r > 0 && ms < best) best = ms;
+    }
+    out[mode] = best;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  cudaStreamDestroy(hi);
   return BALM_OK;
 }
 
