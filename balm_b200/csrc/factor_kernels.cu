@@ -38,6 +38,38 @@ struct StatsArgs {
 // so the serial eigen-solve of one voxel overlaps the loads of the others. Lanes stride over the voxel's
 // observations with two observations (20 independent 8-byte loads) in flight per lane.
 constexpr int STATS_WARPS = STATS_THREADS / 32;
+// The stats row of one voxel: [0..19] eigen data, [20..39] the observation sweep's record with every per-voxel factor
+// folded into the vectors it multiplies (so the sweep spends no instruction on them):
+//   vb, u0, a_k = sqrt(coe |w_k|)/NN u_k (k = 1,2; w_k = 2/(l0 - l_k), bavoxel.hpp:392), ug = 2 coe/NN u0,
+//   uh = sqrt(coe |w_0|) u0 (w_0 = -2/NN^2, bavoxel.hpp:385), f = 2 coe/NN, s0 = vb . u0
+__device__ __forceinline__ void store_stats_row(double *row, double vb0, double vb1, double vb2, const double *u0,
+                                                const double *u1, const double *u2, double inv, double coe,
+                                                const double *lam) {
+  const double c0 = sqrt(2.0 * coe) * inv, c1 = sqrt(2.0 * coe / (lam[1] - lam[0])), c2 = sqrt(2.0 * coe / (lam[2] - lam[0]));
+  double2 *st = reinterpret_cast<double2 *>(row);
+  st[0] = make_double2(vb0, vb1);
+  st[1] = make_double2(vb2, u0[0]);
+  st[2] = make_double2(u0[1], u0[2]);
+  st[3] = make_double2(u1[0], u1[1]);
+  st[4] = make_double2(u1[2], u2[0]);
+  st[5] = make_double2(u2[1], u2[2]);
+  st[6] = make_double2(inv, c0);
+  st[7] = make_double2(c1, c2);
+  st[8] = make_double2(coe, lam[0]);
+  st[9] = make_double2(lam[1], lam[2]);
+  const double f = 2.0 * coe * inv, k1 = c1 * inv, k2 = c2 * inv;
+  st[10] = make_double2(vb0, vb1);
+  st[11] = make_double2(vb2, u0[0]);
+  st[12] = make_double2(u0[1], u0[2]);
+  st[13] = make_double2(k1 * u1[0], k1 * u1[1]);
+  st[14] = make_double2(k1 * u1[2], k2 * u2[0]);
+  st[15] = make_double2(k2 * u2[1], k2 * u2[2]);
+  st[16] = make_double2(f * u0[0], f * u0[1]);
+  st[17] = make_double2(f * u0[2], c0 * u0[0]);
+  st[18] = make_double2(c0 * u0[1], c0 * u0[2]);
+  st[19] = make_double2(f, vb0 * u0[0] + vb1 * u0[1] + vb2 * u0[2]);
+}
+
 template <bool STORE, bool SMEM_POSES>
 __global__ void __launch_bounds__(STATS_THREADS, 3) voxel_stats_kernel(StatsArgs a) {
   extern __shared__ double s_poses[];  // [12 * N] pose table (R column-major, p): 96 B per pose, read per observation
@@ -89,19 +121,7 @@ __global__ void __launch_bounds__(STATS_THREADS, 3) voxel_stats_kernel(StatsArgs
                 acc[3] * inv - vb1 * vb1, acc[4] * inv - vb1 * vb2, acc[5] * inv - vb2 * vb2, lam, u0, u1, u2);
     const double coe = __ldg(a.coe + v);
     res_acc += coe * lam[0];
-    if (STORE && lane == 0) {
-      double *st = a.stats + (v - a.v0) * BALM_STATS_STRIDE;
-      st[0] = vb0; st[1] = vb1; st[2] = vb2;
-      st[3] = u0[0]; st[4] = u0[1]; st[5] = u0[2];
-      st[6] = u1[0]; st[7] = u1[1]; st[8] = u1[2];
-      st[9] = u2[0]; st[10] = u2[1]; st[11] = u2[2];
-      st[12] = inv;
-      st[13] = sqrt(2.0 * coe) * inv;               // sqrt(coe*|w0|), w0 = -2/NN^2 (bavoxel.hpp:385)
-      st[14] = sqrt(2.0 * coe / (lam[1] - lam[0])); // sqrt(coe*|w1|), w1 = 2/(l0-l1) (bavoxel.hpp:392)
-      st[15] = sqrt(2.0 * coe / (lam[2] - lam[0]));
-      st[16] = coe;
-      st[17] = lam[0]; st[18] = lam[1]; st[19] = lam[2];
-    }
+    if (STORE && lane == 0) store_stats_row(a.stats + (v - a.v0) * BALM_STATS_STRIDE, vb0, vb1, vb2, u0, u1, u2, inv, coe, lam);
   }
   if (lane == 0) a.res_part[gw] = res_acc;
 }
@@ -181,20 +201,7 @@ __global__ void __launch_bounds__(128) voxel_eig_kernel(const double *sums, cons
                 acc[3] * inv - vb1 * vb1, acc[4] * inv - vb1 * vb2, acc[5] * inv - vb2 * vb2, lam, u0, u1, u2);
     const double coe = __ldg(coe_all + v);
     res_acc += coe * lam[0];
-    if (STORE) {
-      double2 *st = reinterpret_cast<double2 *>(stats + (v - v0) * BALM_STATS_STRIDE);
-      st[0] = make_double2(vb0, vb1);
-      st[1] = make_double2(vb2, u0[0]);
-      st[2] = make_double2(u0[1], u0[2]);
-      st[3] = make_double2(u1[0], u1[1]);
-      st[4] = make_double2(u1[2], u2[0]);
-      st[5] = make_double2(u2[1], u2[2]);
-      st[6] = make_double2(inv, sqrt(2.0 * coe) * inv);           // [13] sqrt(coe*|w0|), w0 = -2/NN^2 (bavoxel.hpp:385)
-      st[7] = make_double2(sqrt(2.0 * coe / (lam[1] - lam[0])),   // [14] sqrt(coe*|w1|), w1 = 2/(l0-l1) (bavoxel.hpp:392)
-                           sqrt(2.0 * coe / (lam[2] - lam[0])));
-      st[8] = make_double2(coe, lam[0]);
-      st[9] = make_double2(lam[1], lam[2]);
-    }
+    if (STORE) store_stats_row(stats + (v - v0) * BALM_STATS_STRIDE, vb0, vb1, vb2, u0, u1, u2, inv, coe, lam);
   }
   res_acc = warp_sum(res_acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = res_acc;
@@ -236,6 +243,7 @@ struct ObsArgs {
 // One lane = one pose; a warp covers 32 consecutive poses and walks a chunk of voxels, so the observation
 // loads of a dense scene (slot j == pose j) are coalesced and the 27 accumulators stay in registers.
 enum { OBS_FP64 = 0, OBS_MAXONLY = 1, OBS_INT8 = 2, OBS_FUSED = 3 };
+constexpr int OBS_STAGES = 4;  // cp.async ring depth of the dense sweep (iterations in flight per warp)
 // MODE: OBS_FP64    writes fp64 G' + gradient / diagonal blocks                          [fp64 SYRK path]
 //       OBS_MAXONLY first sweep of the tensor path: column maxima of G' (-> power-of-two column scales) and the
 //                   gradient / diagonal-block accumulators (kept here so that the second sweep is lean)
@@ -245,8 +253,8 @@ enum { OBS_FP64 = 0, OBS_MAXONLY = 1, OBS_INT8 = 2, OBS_FUSED = 3 };
 //                   step moves the column maxima by far less than the factor 2 of headroom a balanced top digit
 //                   has); tc_scale_kernel checks the new maxima against the scales used and, if a column overflowed
 //                   or lost precision, re-arms the OBS_INT8 sweep (which otherwise returns at once)
-template <bool DENSE, int MODE, int WPC = 4>
-__global__ void __launch_bounds__(WPC * 32) obs_pass_kernel(ObsArgs a) {
+template <bool DENSE, int MODE, int WPC = 4, int MINB = 2>
+__global__ void __launch_bounds__(WPC * 32, MINB) obs_pass_kernel(ObsArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile = blockIdx.y * WPC + warp;
   const int i = tile * 32 + lane;
@@ -277,42 +285,68 @@ __global__ void __launch_bounds__(WPC * 32) obs_pass_kernel(ObsArgs a) {
     t1 = t0 + a.chunk < e ? t0 + a.chunk : e;
   }
 
-  // software prefetch: the ten observation words of iteration t+1 are requested before iteration t is computed,
-  // so one global-memory round trip is always in flight per warp (dense scenes: s = v*N + i, no index loads)
-  double onext[10];
+  // Observation prefetch. Dense scenes (s = v*N + i, no index loads): the ten words of the next OBS_STAGES iterations
+  // are in flight as cp.async copies into a per-warp shared-memory ring -- with 8 resident warps per SM (register
+  // file) one iteration ahead kept only ~20 KB per SM in flight, which is what bounded the sweep at half the HBM rate;
+  // every lane copies and later reads its own words, so no barrier is involved. Pose-major lists (sparse): the ten
+  // words of iteration t+1 are requested into registers before iteration t is computed.
+  __shared__ __align__(16) double s_obs[DENSE ? WPC : 1][DENSE ? OBS_STAGES : 1][10][32];
+  double onext[DENSE ? 1 : 10];
+  auto stage = [&](long long t, int slot) {
+    if (t < t1 && active) {
+      const double *src = a.obs + (t * (long long)a.N + i);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_obs[DENSE ? warp : 0][DENSE ? slot : 0][0][lane]);
+#pragma unroll
+      for (int c = 0; c < 10; c++)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + c * 256), "l"(src + c * a.Kp) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");  // one group per call, empty or not: uniform accounting
+  };
   auto issue = [&](long long t, double *dst) {
     if (t < t1) {
-      long long s;
-      if (DENSE) s = t * (long long)a.N + i;
-      else s = a.csc_obs[t];
-      if (!DENSE || active) {
+      const long long s = a.csc_obs[t];
 #pragma unroll
-        for (int c = 0; c < 10; c++) dst[c] = ld_stream(a.obs + c * a.Kp + s);
-      }
+      for (int c = 0; c < 10; c++) dst[c] = ld_stream(a.obs + c * a.Kp + s);
     }
   };
-  issue(t0, onext);
+  int slot = 0;
+  if (DENSE) {
+#pragma unroll
+    for (int d = 0; d < OBS_STAGES; d++) stage(t0 + d, d);
+  } else {
+    issue(t0, onext);
+  }
   // dense scenes: the voxel is warp-uniform, so its 20 stats words are fetched ONE ITERATION AHEAD by lanes 0..19
   // (one word each), parked in a per-warp shared-memory slot at the top of the iteration and read back as
   // broadcasts -- instead of ten L2-latency loads whose result is needed immediately
-  __shared__ __align__(16) double s_stats[WPC][2][BALM_STATS_STRIDE];
+  __shared__ __align__(16) double s_stats[WPC][2][BALM_SWEEP_WORDS];
   double st_next = 0.0;
-  if (DENSE && lane < BALM_STATS_STRIDE && t0 < t1) st_next = __ldg(a.stats + (t0 - a.v0) * BALM_STATS_STRIDE + lane);
+  if (DENSE && lane < BALM_SWEEP_WORDS && t0 < t1) st_next = __ldg(a.stats + (t0 - a.v0) * BALM_STATS_STRIDE + BALM_SWEEP_OFF + lane);
   for (long long t = t0; t < t1; t++) {
     long long v;
     double o[10];
+    if (DENSE) {
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(OBS_STAGES - 1) : "memory");  // this iteration's group has landed
+      if (active) {
 #pragma unroll
-    for (int c = 0; c < 10; c++) o[c] = onext[c];
-    issue(t + 1, onext);
-    double st[BALM_STATS_STRIDE];
+        for (int c = 0; c < 10; c++) o[c] = s_obs[DENSE ? warp : 0][DENSE ? slot : 0][c][lane];
+      }
+      stage(t + OBS_STAGES, slot);  // refill the slot just read
+      slot = (slot + 1) % OBS_STAGES;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 10; c++) o[c] = onext[c];
+      issue(t + 1, onext);
+    }
+    double st[BALM_SWEEP_WORDS];
     if (DENSE) {
       v = t;
       double *slot = s_stats[warp][(int)(t & 1)];
-      if (lane < BALM_STATS_STRIDE) slot[lane] = st_next;
+      if (lane < BALM_SWEEP_WORDS) slot[lane] = st_next;
       __syncwarp();
-      if (lane < BALM_STATS_STRIDE && t + 1 < t1) st_next = __ldg(a.stats + (t + 1 - a.v0) * BALM_STATS_STRIDE + lane);
+      if (lane < BALM_SWEEP_WORDS && t + 1 < t1) st_next = __ldg(a.stats + (t + 1 - a.v0) * BALM_STATS_STRIDE + BALM_SWEEP_OFF + lane);
 #pragma unroll
-      for (int c = 0; c < BALM_STATS_STRIDE / 2; c++) {
+      for (int c = 0; c < BALM_SWEEP_WORDS / 2; c++) {
         const double2 x = reinterpret_cast<const double2 *>(slot)[c];
         st[2 * c] = x.x;
         st[2 * c + 1] = x.y;
@@ -320,56 +354,75 @@ __global__ void __launch_bounds__(WPC * 32) obs_pass_kernel(ObsArgs a) {
       if (!active) continue;
     } else {
       v = a.csc_vox[t];
-      const double2 *st2 = reinterpret_cast<const double2 *>(a.stats + (v - a.v0) * BALM_STATS_STRIDE);
+      const double2 *st2 = reinterpret_cast<const double2 *>(a.stats + (v - a.v0) * BALM_STATS_STRIDE + BALM_SWEEP_OFF);
 #pragma unroll
-      for (int c = 0; c < BALM_STATS_STRIDE / 2; c++) {
+      for (int c = 0; c < BALM_SWEEP_WORDS / 2; c++) {
         const double2 x = __ldg(st2 + c);
         st[2 * c] = x.x;
         st[2 * c + 1] = x.y;
       }
     }
-    const WC w = world_cluster(o, r, p);
-    const double *vb = st, *u0 = st + 3, *u1 = st + 6, *u2 = st + 9;
-    const double inv = st[12], coe = st[16];
-    // M_i = [P' - v' vb^T ; (v' - n vb)^T]  (= TC_i * [R_i | p_i - vb]^T, bavoxel.hpp:368-370)
-    const double m00 = w.p00 - w.v0 * vb[0], m01 = w.p01 - w.v0 * vb[1], m02 = w.p02 - w.v0 * vb[2];
-    const double m10 = w.p01 - w.v1 * vb[0], m11 = w.p11 - w.v1 * vb[1], m12 = w.p12 - w.v1 * vb[2];
-    const double m20 = w.p02 - w.v2 * vb[0], m21 = w.p12 - w.v2 * vb[1], m22 = w.p22 - w.v2 * vb[2];
-    const double mb[3] = {w.v0 - w.n * vb[0], w.v1 - w.n * vb[1], w.v2 - w.n * vb[2]};
-    double tk[3][3], sk[3];
-    const double *uu[3] = {u0, u1, u2};
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      tk[k][0] = m00 * uu[k][0] + m01 * uu[k][1] + m02 * uu[k][2];
-      tk[k][1] = m10 * uu[k][0] + m11 * uu[k][1] + m12 * uu[k][2];
-      tk[k][2] = m20 * uu[k][0] + m21 * uu[k][1] + m22 * uu[k][2];
-      sk[k] = mb[0] * uu[k][0] + mb[1] * uu[k][1] + mb[2] * uu[k][2];
-    }
-    // g_k^i = (U_k M u_0 + U_0 M u_k)/NN, U_k = [hat(-u_k) 0; 0 u_k]  (bavoxel.hpp:371-378)
-    double gk[3][6];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      double c1[3], c2[3];
-      cross3(uu[k], tk[0], c1);
-      cross3(u0, tk[k], c2);
-#pragma unroll
-      for (int q = 0; q < 3; q++) {
-        gk[k][q] = -(c1[q] + c2[q]) * inv;
-        gk[k][3 + q] = (uu[k][q] * sk[0] + u0[q] * sk[k]) * inv;
-      }
-    }
-    // a_i = (U_0 TC_i)[:,3] = [-u0 x v' ; n u0]  (bavoxel.hpp:380)
-    const double vw[3] = {w.v0, w.v1, w.v2};
-    double cuv[3];
-    cross3(u0, vw, cuv);
-    const double ai[6] = {-cuv[0], -cuv[1], -cuv[2], w.n * u0[0], w.n * u0[1], w.n * u0[2]};
-
-    // ---- G' rows (3 per voxel), 6 contiguous values per pose ----
+    // ---- per-voxel sweep record (written by the eigen half of the stats pass, words 20..39 of the stats row) ----
+    //   vb = mean, u0 = plane normal, a_k = sqrt(coe |w_k|)/NN u_k (k = 1, 2: the G' rows come out scaled),
+    //   ug = 2 coe/NN u0, uh = sqrt(2 coe)/NN u0, f = 2 coe/NN, s0 = vb . u0
+    const double *vb = st, *u0 = st + 3, *a1 = st + 6, *a2 = st + 9, *ug = st + 12, *uh = st + 15;
+    const double f = st[18], s0 = st[19];
+    // ---- world-frame cluster (PointCluster::transform, tools.hpp:333-339): P' = R P R^T + v' p^T + p (R v)^T ----
+    const double rv0 = r[0] * o[6] + r[1] * o[7] + r[2] * o[8];
+    const double rv1 = r[3] * o[6] + r[4] * o[7] + r[5] * o[8];
+    const double rv2 = r[6] * o[6] + r[7] * o[7] + r[8] * o[8];
+    const double n = o[9];
+    const double vw[3] = {rv0 + n * p[0], rv1 + n * p[1], rv2 + n * p[2]};
+    double p00, p01, p02, p11, p12, p22;
     {
-      const double c0 = st[13], c1s = st[14], c2s = st[15];
+      const double x00 = r[0] * o[0] + r[1] * o[1] + r[2] * o[2];
+      const double x01 = r[0] * o[1] + r[1] * o[3] + r[2] * o[4];
+      const double x02 = r[0] * o[2] + r[1] * o[4] + r[2] * o[5];
+      const double x10 = r[3] * o[0] + r[4] * o[1] + r[5] * o[2];
+      const double x11 = r[3] * o[1] + r[4] * o[3] + r[5] * o[4];
+      const double x12 = r[3] * o[2] + r[4] * o[4] + r[5] * o[5];
+      const double x20 = r[6] * o[0] + r[7] * o[1] + r[8] * o[2];
+      const double x21 = r[6] * o[1] + r[7] * o[3] + r[8] * o[4];
+      const double x22 = r[6] * o[2] + r[7] * o[4] + r[8] * o[5];
+      p00 = x00 * r[0] + x01 * r[1] + x02 * r[2] + vw[0] * p[0] + p[0] * rv0;
+      p01 = x00 * r[3] + x01 * r[4] + x02 * r[5] + vw[0] * p[1] + p[0] * rv1;
+      p02 = x00 * r[6] + x01 * r[7] + x02 * r[8] + vw[0] * p[2] + p[0] * rv2;
+      p11 = x10 * r[3] + x11 * r[4] + x12 * r[5] + vw[1] * p[1] + p[1] * rv1;
+      p12 = x10 * r[6] + x11 * r[7] + x12 * r[8] + vw[1] * p[2] + p[1] * rv2;
+      p22 = x20 * r[6] + x21 * r[7] + x22 * r[8] + vw[2] * p[2] + p[2] * rv2;
+    }
+    // M = [P' - v' vb^T ; (v' - n vb)^T]  (= TC_i * [R_i | p_i - vb]^T, bavoxel.hpp:368-370)
+    const double m00 = p00 - vw[0] * vb[0], m01 = p01 - vw[0] * vb[1], m02 = p02 - vw[0] * vb[2];
+    const double m10 = p01 - vw[1] * vb[0], m11 = p11 - vw[1] * vb[1], m12 = p12 - vw[1] * vb[2];
+    const double m20 = p02 - vw[2] * vb[0], m21 = p12 - vw[2] * vb[1], m22 = p22 - vw[2] * vb[2];
+    const double mb[3] = {vw[0] - n * vb[0], vw[1] - n * vb[1], vw[2] - n * vb[2]};
+    const double t0[3] = {m00 * u0[0] + m01 * u0[1] + m02 * u0[2], m10 * u0[0] + m11 * u0[1] + m12 * u0[2],
+                          m20 * u0[0] + m21 * u0[1] + m22 * u0[2]};
+    const double s0p = mb[0] * u0[0] + mb[1] * u0[1] + mb[2] * u0[2];
+
+    // ---- G' rows (3 per voxel), 6 contiguous values per pose:  row 0 = sqrt(coe|w0|) a_i, a_i = [-u0 x v' ; n u0]
+    // (bavoxel.hpp:380,385); rows k = 1,2 = sqrt(coe|w_k|) g_k^i, g_k^i = (U_k M u_0 + U_0 M u_k)/NN with
+    // U_k = [hat(-u_k) 0; 0 u_k] (bavoxel.hpp:371-378,392) -- the scale factors ride on the record's vectors ----
+    {
       double gv[3][6];
+      gv[0][0] = vw[1] * uh[2] - vw[2] * uh[1];
+      gv[0][1] = vw[2] * uh[0] - vw[0] * uh[2];
+      gv[0][2] = vw[0] * uh[1] - vw[1] * uh[0];
+      gv[0][3] = n * uh[0]; gv[0][4] = n * uh[1]; gv[0][5] = n * uh[2];
 #pragma unroll
-      for (int q = 0; q < 6; q++) { gv[0][q] = c0 * ai[q]; gv[1][q] = c1s * gk[1][q]; gv[2][q] = c2s * gk[2][q]; }
+      for (int k = 1; k < 3; k++) {
+        const double *ak = k == 1 ? a1 : a2;
+        const double ma[3] = {m00 * ak[0] + m01 * ak[1] + m02 * ak[2], m10 * ak[0] + m11 * ak[1] + m12 * ak[2],
+                              m20 * ak[0] + m21 * ak[1] + m22 * ak[2]};
+        const double sa = mb[0] * ak[0] + mb[1] * ak[1] + mb[2] * ak[2];
+        // -(a_k x t0 + u0 x (M a_k)) = t0 x a_k + (M a_k) x u0
+        gv[k][0] = t0[1] * ak[2] - t0[2] * ak[1] + ma[1] * u0[2] - ma[2] * u0[1];
+        gv[k][1] = t0[2] * ak[0] - t0[0] * ak[2] + ma[2] * u0[0] - ma[0] * u0[2];
+        gv[k][2] = t0[0] * ak[1] - t0[1] * ak[0] + ma[0] * u0[1] - ma[1] * u0[0];
+        gv[k][3] = ak[0] * s0p + u0[0] * sa;
+        gv[k][4] = ak[1] * s0p + u0[1] * sa;
+        gv[k][5] = ak[2] * s0p + u0[2] * sa;
+      }
       if (MODE == OBS_FP64) {
         double *g0 = a.G + (size_t)(3 * (v - a.v0)) * a.ldg + 6 * i;
 #pragma unroll
@@ -414,46 +467,38 @@ __global__ void __launch_bounds__(WPC * 32) obs_pass_kernel(ObsArgs a) {
       }
     }
     if (MODE == OBS_INT8) continue;  // gradient and diagonal blocks were accumulated by the first sweep
-    // ---- gradient (bavoxel.hpp:381) ----
-#pragma unroll
-    for (int q = 0; q < 6; q++) acc[q] += coe * gk[0][q];
-    // ---- diagonal block: coe*( 2/NN * U0 TCT U0^T + [[Ell+Ell^T,0],[0,0]] )  (bavoxel.hpp:387-388,397-402) ----
+    // ---- gradient: coe g_0^i = [t0 x ug ; ug (mb . u0)]  (bavoxel.hpp:381) ----
+    acc[0] += t0[1] * ug[2] - t0[2] * ug[1];
+    acc[1] += t0[2] * ug[0] - t0[0] * ug[2];
+    acc[2] += t0[0] * ug[1] - t0[1] * ug[0];
+    acc[3] += ug[0] * s0p; acc[4] += ug[1] * s0p; acc[5] += ug[2] * s0p;
+    // ---- diagonal block coe*( 2/NN * U0 TCT U0^T + [[Ell+Ell^T,0],[0,0]] )  (bavoxel.hpp:387-388,397-402), upper
+    // triangle in row-major order acc[6..26]. Columns 3..5: f a_i u0^T. Top-left 3x3: with |u0| = 1,
+    //   hat(u0) P' hat(u0)^T = -P' + u0 q^T + q u0^T - tr(P') u0 u0^T + (tr(P') - u0.q) I,  q = P' u0 = t0 + s0 v',
+    // and Ell + Ell^T = (u0 t0^T + t0 u0^T - 2 (t0.u0) I)/NN, so the block is
+    //   -f P' + ug z^T + z ug^T + f kappa I,  z = 1.5 t0 + s0 v' - tr(P')/2 u0,  kappa = tr(P') - 2 u0.t0 - s0 u0.v' ----
     {
-      const double f = 2.0 * inv * coe;
-      // X = hat(u0) * P'
-      const double Pw[3][3] = {{w.p00, w.p01, w.p02}, {w.p01, w.p11, w.p12}, {w.p02, w.p12, w.p22}};
-      double X[3][3];
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const double col[3] = {Pw[0][c], Pw[1][c], Pw[2][c]};
-        double xc[3];
-        cross3(u0, col, xc);
-        X[0][c] = xc[0]; X[1][c] = xc[1]; X[2][c] = xc[2];
-      }
-      // TL = X * hat(u0)^T : row r = u0 x X[r,:]
-      double TL[3][3];
-#pragma unroll
-      for (int rr = 0; rr < 3; rr++) cross3(u0, X[rr], TL[rr]);
-      // Ell + Ell^T = (u0 t0^T + t0 u0^T - 2 (t0.u0) I)/NN with t0 = M[0:3,:] u0
-      const double *t0v = tk[0];
-      const double tu = t0v[0] * u0[0] + t0v[1] * u0[1] + t0v[2] * u0[2];
-      const double fe = coe * inv;
-      int q = 6;
-#pragma unroll
-      for (int rr = 0; rr < 6; rr++) {
-#pragma unroll
-        for (int cc = rr; cc < 6; cc++) {
-          double val;
-          if (rr < 3 && cc < 3) {
-            val = f * TL[rr][cc] + fe * (u0[rr] * t0v[cc] + t0v[rr] * u0[cc] - (rr == cc ? 2.0 * tu : 0.0));
-          } else if (rr < 3) {
-            val = f * (-cuv[rr] * u0[cc - 3]);
-          } else {
-            val = f * w.n * u0[rr - 3] * u0[cc - 3];
-          }
-          acc[q++] += val;
-        }
-      }
+      const double ag[6] = {vw[1] * ug[2] - vw[2] * ug[1], vw[2] * ug[0] - vw[0] * ug[2], vw[0] * ug[1] - vw[1] * ug[0],
+                            n * ug[0], n * ug[1], n * ug[2]};
+      const double trp = p00 + p11 + p22, hh = 0.5 * trp;
+      const double z[3] = {1.5 * t0[0] + s0 * vw[0] - hh * u0[0], 1.5 * t0[1] + s0 * vw[1] - hh * u0[1],
+                           1.5 * t0[2] + s0 * vw[2] - hh * u0[2]};
+      const double ut = u0[0] * t0[0] + u0[1] * t0[1] + u0[2] * t0[2];
+      const double uv = u0[0] * vw[0] + u0[1] * vw[1] + u0[2] * vw[2];
+      const double fk = f * (trp - 2.0 * ut - s0 * uv);
+      // rows 0..2: [ TL(rr, rr..2) | ag[rr] u0^T ]; rows 3..5: ag[rr] u0[rr-3 ..]
+      acc[6]  += fk - f * p00 + 2.0 * (ug[0] * z[0]);
+      acc[7]  += ug[0] * z[1] + z[0] * ug[1] - f * p01;
+      acc[8]  += ug[0] * z[2] + z[0] * ug[2] - f * p02;
+      acc[9]  += ag[0] * u0[0]; acc[10] += ag[0] * u0[1]; acc[11] += ag[0] * u0[2];
+      acc[12] += fk - f * p11 + 2.0 * (ug[1] * z[1]);
+      acc[13] += ug[1] * z[2] + z[1] * ug[2] - f * p12;
+      acc[14] += ag[1] * u0[0]; acc[15] += ag[1] * u0[1]; acc[16] += ag[1] * u0[2];
+      acc[17] += fk - f * p22 + 2.0 * (ug[2] * z[2]);
+      acc[18] += ag[2] * u0[0]; acc[19] += ag[2] * u0[1]; acc[20] += ag[2] * u0[2];
+      acc[21] += ag[3] * u0[0]; acc[22] += ag[3] * u0[1]; acc[23] += ag[3] * u0[2];
+      acc[24] += ag[4] * u0[1]; acc[25] += ag[4] * u0[2];
+      acc[26] += ag[5] * u0[2];
     }
   }
   if (MODE != OBS_INT8 && active && a.colmax) {

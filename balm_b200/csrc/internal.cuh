@@ -8,7 +8,10 @@
 
 #define BALM_SCAL_RCUR 16
 #define BALM_SCAL_RTRIAL 17
-#define BALM_STATS_STRIDE 20  // doubles per voxel in the stats table
+#define BALM_STATS_STRIDE 40  // doubles per voxel in the stats table: [0..19] eigen data (vb, u0..u2, 1/NN, the three
+                              // sqrt(coe|w_k|), coe, lambda), [20..39] the observation sweep's record (see obs_pass_kernel)
+#define BALM_SWEEP_OFF 20
+#define BALM_SWEEP_WORDS 20
 #define BALM_ACC 33           // per-pose accumulators of the observation pass: g(6) + sym 6x6 diag block (21)
                               // + exact fp64 sums of squares of the 6 G' columns (diagonal of G'^T G')
 #define BALM_NB 64            // LDL^T panel width
