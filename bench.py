@@ -55,7 +55,8 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.rows = []      # (sm_mhz, sm_max_mhz, set of reasons)
+        self.rows = []      # (sm_mhz, sm_max_mhz, set of reasons[, board power in W])
+        self.power_limit_w = None
         self.stop_flag = False
         self.thread = None
         self.proc = None
@@ -63,12 +64,20 @@ class ClockSampler:
     def _nvml_loop(self, nv, h):
         bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            self.power_limit_w = nv.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append((float(sm), float(mx), {k for k, b in bits.items() if r & b}))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                self.rows.append((float(sm), float(mx), {k for k, b in bits.items() if r & b}, pw))
             except Exception:
                 pass
             time.sleep(0.02)
@@ -104,8 +113,12 @@ class ClockSampler:
             if len(f) < 7:
                 continue
             try:
+                try:
+                    pw = float(f[2])
+                except ValueError:
+                    pw = None
                 self.rows.append((float(f[0]), float(f[1]),
-                                  {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
+                                  {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}, pw))
             except ValueError:
                 continue
 
@@ -129,8 +142,13 @@ class ClockSampler:
         reasons = set()
         for r in rows:
             reasons |= r[2]
-        return {"sm_mhz": float(np.median([r[0] for r in rows])), "sm_max_mhz": max(r[1] for r in rows),
-                "reasons": sorted(reasons), "samples": len(rows)}
+        out = {"sm_mhz": float(np.median([r[0] for r in rows])), "sm_max_mhz": max(r[1] for r in rows),
+               "reasons": sorted(reasons), "samples": len(rows)}
+        pw = [r[3] for r in rows if len(r) > 3 and r[3] is not None]
+        if pw:  # board power under load next to the enforced limit: the SYRK runs AT the limit (sw_power_cap)
+            out["power_w"] = float(np.median(pw))
+            out["power_limit_w"] = self.power_limit_w
+        return out
 
 
 def numpy_sample(n_poses, n_voxels, seed=SEED):
