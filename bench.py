@@ -238,11 +238,33 @@ class CpuArm:
                 f"(bavoxel.hpp:1027), residual + LDL^T 1 thread; gcc -O3 without -march=native (CMakeLists.txt:9)")
 
 
+def ref_headers_check(n_poses, m_small, port_eval_s):
+    """The reference's OWN divide_thread_left (bavoxel.hpp:1025-1059, compiled from /root/reference's headers against
+    stand-in Eigen into oracle/_ref/libbalm_ref.so, when that file travelled here) on the small sample, next to the port's
+    time for the same call. A plausibility check of the port's speed, not a baseline: the stand-in has none of Eigen's
+    vectorised kernels, and the reference leaks its per-observation `Co` blocks (bavoxel.hpp:312-320)."""
+    try:
+        from oracle import ref_py
+        if not ref_py.available():
+            return None
+        rp, pi, ob, co, init = numpy_sample(n_poses, m_small)
+        prob = ref_py.Problem(n_poses, rp, pi, ob)
+        t0 = time.perf_counter()
+        prob.divide_thread_left(init)
+        return {"ref_headers_standin_eigen_eval_s": time.perf_counter() - t0, "port_eval_s": port_eval_s,
+                "sample_voxels": m_small, "threads": 4}
+    except Exception as e:  # the check must never take the bench down
+        return {"error": str(e)[:120]}
+
+
 def cpu_baseline_once(n_poses, voxels_total, m_small, m_large):
     arm = CpuArm(n_poses, m_small, m_large)
     _, t_iter, detail = arm.step(voxels_total)
     out = {"value": 1.0 / t_iter, "unit": "iter/s", "cores": 4, "kind": "port", "extrapolated": True,
            "sample": arm.describe(voxels_total), "detail": detail}
+    chk = ref_headers_check(n_poses, m_small, detail["t_eval_s"][0])
+    if chk:
+        out["ref_headers_check"] = chk
     try:  # labelled NON-reference column: the same port compiled with -march=native
         _, t_nat, _ = CpuArm(n_poses, m_small, m_large, native=True).step(voxels_total)
         out["value_march_native"] = 1.0 / t_nat
@@ -270,6 +292,7 @@ def run_reference(args, rank, world):
             its.append(t)
     t_iter = float(np.mean(its))
     val = 1.0 / t_iter
+    chk = ref_headers_check(n, args.cpu_sample_small, detail["t_eval_s"][0])  # once, outside the timed steps
     line = {
         "impl": "reference", "metric": "ba_iterations_per_sec", "value": val, "unit": "iter/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(wall)),
@@ -282,6 +305,8 @@ def run_reference(args, rank, world):
                          "sample": arm.describe(m), "detail": detail},
         "e2e": {"value": val, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if chk:
+        line["cpu_baseline"]["ref_headers_check"] = chk
     print(json.dumps(line), flush=True)
 
 
