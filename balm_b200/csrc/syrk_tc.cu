@@ -487,59 +487,21 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw64(uint32_t smem_addr) {
   return d;
 }
 
-// MN-major, SWIZZLE_32B: 32 contiguous bytes along N per k row, 8 k rows per 256-byte atom, SBO = next 8 k rows. Used for
-// the LAST block column when it holds at most 64 valid columns (n = 3000: 56): the pair then issues N = 64 MMAs, each CTA
-// holding 32 columns of the B block -- half the tensor work of a full tile for the 2 x nb tiles of that column.
-constexpr int B32_TILE_BYTES = KS * 32;  // 2048: one plane of this CTA's 32 columns of the B block, one stage
-__device__ __forceinline__ uint64_t make_desc_mn_sw32(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((B32_TILE_BYTES >> 4) & 0x3FFF) << 16;    // LBO (unused: one 32-byte block along N)
-  d |= (uint64_t)((256 >> 4) & 0x3FFF) << 32;               // SBO
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)6 << 61;                                   // SWIZZLE_32B
-  return d;
-}
-
-// the MMAs of one pipeline stage (KS contraction rows): S(S+1)/2 digit-pair products per 32-row K step, fully unrolled
-template <int S, bool N64>
-__device__ __forceinline__ void mma_stage_2sm(uint32_t base, uint32_t tmem_base, uint32_t acc0) {
-  constexpr uint32_t idesc = make_idesc_i8(2 * TILE, N64 ? TILE / 2 : TILE);  // M = 256 across the pair, N = 128 or 64
-  constexpr uint32_t PLANE_U = PLANE_TILE_BYTES >> 4, BPLANE_U = BHALF_TILE_BYTES >> 4;
-  constexpr uint32_t KK_A = (UMMA_K * TILE) >> 4, KK_B = (UMMA_K * (N64 ? 32 : TILE / 2)) >> 4;
-  const uint64_t dsc_b = N64 ? make_desc_mn_sw32(0) : make_desc_mn_sw64(0);
-  const uint64_t hi_a = make_desc_mn_sw128(0) & 0xFFFFFFFF00000000ull, hi_b = dsc_b & 0xFFFFFFFF00000000ull;
-  const uint32_t fx_a = (uint32_t)(make_desc_mn_sw128(0) & 0xFFFFFFFFull), fx_b = (uint32_t)(dsc_b & 0xFFFFFFFFull);
-  const uint32_t lo_a = fx_a + base, lo_b = fx_b + base + S * PLANE_U;
-#pragma unroll
-  for (int kk = 0; kk < KS / UMMA_K; kk++) {
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      const uint64_t da = hi_a | (uint64_t)(lo_a + s * PLANE_U + kk * KK_A);
-#pragma unroll
-      for (int tt = 0; tt + s < S; tt++) {
-        const uint64_t db = hi_b | (uint64_t)(lo_b + tt * BPLANE_U + kk * KK_B);
-        const uint32_t acc = (s > 0 || kk > 0) ? 1u : acc0;
-        if (S - s == 1) tc_mma_i8_2sm<0>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
-        else if (tt == 0) tc_mma_i8_2sm<1>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
-        else if (tt == S - s - 1) tc_mma_i8_2sm<3>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
-        else tc_mma_i8_2sm<2>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
-      }
-    }
-  }
-}
-
 template <int S>
 __device__ __forceinline__ void mma_issue_loop_2sm(const TcArgs &a, uint8_t *stage_base, uint64_t *full_bar,
                                                    uint64_t *empty_bar, uint64_t *tmem_full, uint64_t *tmem_empty,
                                                    uint32_t tmem_base, int n_items, int64_t per, int first, int stride) {
+  constexpr uint32_t idesc = make_idesc_i8(2 * TILE, TILE);  // M = 256 across the pair, N = 128
+  constexpr uint32_t PLANE_U = PLANE_TILE_BYTES >> 4, BPLANE_U = BHALF_TILE_BYTES >> 4;
+  constexpr uint32_t KK_A = (UMMA_K * TILE) >> 4, KK_B = (UMMA_K * (TILE / 2)) >> 4;
+  const uint64_t hi_a = make_desc_mn_sw128(0) & 0xFFFFFFFF00000000ull, hi_b = make_desc_mn_sw64(0) & 0xFFFFFFFF00000000ull;
+  const uint32_t fx_a = (uint32_t)(make_desc_mn_sw128(0) & 0xFFFFFFFFull), fx_b = (uint32_t)(make_desc_mn_sw64(0) & 0xFFFFFFFFull);
   constexpr int nst = stages2_for(S), sbytes = stage2_bytes_for(S);
   int st = 0;
   uint32_t ph = 0, n_done = 0;
   bool alive = true;
   for (int item = first; alive && item < n_items; item += stride, n_done++) {
     const int sp = item / a.n_pairs;
-    const bool n64 = (a.pairs[item % a.n_pairs].y & 4) != 0;
     const int64_t k_begin = (int64_t)sp * per;
     int64_t k_end = k_begin + per;
     if (k_end > a.rows) k_end = a.rows;
@@ -550,10 +512,25 @@ __device__ __forceinline__ void mma_issue_loop_2sm(const TcArgs &a, uint8_t *sta
       if (!__all_sync(0xffffffffu, mbar_wait(&full_bar[st], ph, a.err))) { alive = false; break; }
       tc_fence_after();
       const uint32_t base = (smem_u32(stage_base + st * sbytes) & 0x3FFFF) >> 4;
+      const uint32_t lo_a = fx_a + base, lo_b = fx_b + base + S * PLANE_U;
       const uint32_t acc0 = ks > 0 ? 1u : 0u;
       if (elect_one()) {
-        if (n64) mma_stage_2sm<S, true>(base, tmem_base, acc0);
-        else mma_stage_2sm<S, false>(base, tmem_base, acc0);
+#pragma unroll
+        for (int kk = 0; kk < KS / UMMA_K; kk++) {
+#pragma unroll
+          for (int s = 0; s < S; s++) {
+            const uint64_t da = hi_a | (uint64_t)(lo_a + s * PLANE_U + kk * KK_A);
+#pragma unroll
+            for (int tt = 0; tt + s < S; tt++) {
+              const uint64_t db = hi_b | (uint64_t)(lo_b + tt * BPLANE_U + kk * KK_B);
+              const uint32_t acc = (s > 0 || kk > 0) ? 1u : acc0;
+              if (S - s == 1) tc_mma_i8_2sm<0>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+              else if (tt == 0) tc_mma_i8_2sm<1>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+              else if (tt == S - s - 1) tc_mma_i8_2sm<3>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+              else tc_mma_i8_2sm<2>(tmem_base + (s + tt) * TILE, da, db, idesc, acc);
+            }
+          }
+        }
         tc_commit_2sm_mc(&empty_bar[st], 3);  // frees this stage in both CTAs
       }
       __syncwarp();
@@ -564,8 +541,7 @@ __device__ __forceinline__ void mma_issue_loop_2sm(const TcArgs &a, uint8_t *sta
   }
 }
 
-__device__ __forceinline__ void syrk_tc_2sm_body(const CUtensorMap &tmap, const CUtensorMap &tmap_b64,
-                                                 const CUtensorMap &tmap_b32, const TcArgs &a) {
+__device__ __forceinline__ void syrk_tc_2sm_body(const CUtensorMap &tmap, const CUtensorMap &tmap_b64, const TcArgs &a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *stage_base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_base + RING_BYTES);
@@ -608,8 +584,6 @@ __device__ __forceinline__ void syrk_tc_2sm_body(const CUtensorMap &tmap, const 
         const int2 pr = a.pairs[item % a.n_pairs];
         const int sp = item / a.n_pairs;
         const int bi = (pr.x >> (rank ? 16 : 0)) & 255, bj = (pr.x >> 8) & 255;
-        const bool n64 = (pr.y & 4) != 0;  // last block column with <= 64 valid columns: 32 of them per CTA
-        const uint32_t tx = n64 ? 2u * S * (PLANE_TILE_BYTES + B32_TILE_BYTES) : 2u * sbytes;
         const int64_t k_begin = (int64_t)sp * per;
         int64_t k_end = k_begin + per;
         if (k_end > a.rows) k_end = a.rows;
@@ -617,16 +591,12 @@ __device__ __forceinline__ void syrk_tc_2sm_body(const CUtensorMap &tmap, const 
         for (int ks = 0; ks < nsteps; ks++) {
           if (!mbar_wait(&empty_bar[st], ph ^ 1, a.err)) { alive = false; break; }
           uint8_t *sb = stage_base + st * sbytes;
-          if (rank == 0) mbar_expect_tx(&full_bar[st], tx);  // bytes of BOTH CTAs land on the leader's barrier
+          if (rank == 0) mbar_expect_tx(&full_bar[st], 2 * sbytes);  // bytes of BOTH CTAs land on the leader's barrier
           const int krow = (int)(k_begin + (int64_t)ks * KS);
           for (int s = 0; s < S; s++) {
             tma_load_3d_2sm(sb + s * PLANE_TILE_BYTES, &tmap, &full_bar[st], bi * TILE, krow, s);
-            if (n64)
-              tma_load_3d_2sm(sb + S * PLANE_TILE_BYTES + s * BHALF_TILE_BYTES, &tmap_b32, &full_bar[st],
-                              bj * TILE + (int)rank * 32, krow, s);
-            else
-              tma_load_3d_2sm(sb + S * PLANE_TILE_BYTES + s * BHALF_TILE_BYTES, &tmap_b64, &full_bar[st],
-                              bj * TILE + (int)rank * (TILE / 2), krow, s);
+            tma_load_3d_2sm(sb + S * PLANE_TILE_BYTES + s * BHALF_TILE_BYTES, &tmap_b64, &full_bar[st],
+                            bj * TILE + (int)rank * (TILE / 2), krow, s);
           }
           if (++st == nst) { st = 0; ph ^= 1; }
         }
@@ -649,7 +619,6 @@ __device__ __forceinline__ void syrk_tc_2sm_body(const CUtensorMap &tmap, const 
       const int sp = item / a.n_pairs;
       const int bi = (pr.x >> (rank ? 16 : 0)) & 255, bj = (pr.x >> 8) & 255;
       const bool store = !((pr.y & 2) && rank == 1);
-      const bool n64 = (pr.y & 4) != 0;  // N = 64 product: accumulator columns 64..127 were not written (zero columns of H)
       const bool flipped = bi > bj;  // computed as (A = bi, B = bj) with bi > bj: the transpose of tile (bj, bi)
       const int ti = flipped ? bj : bi, tj = flipped ? bi : bj;
       const int t = ti * a.nb - ti * (ti - 1) / 2 + (tj - ti);
@@ -664,7 +633,7 @@ __device__ __forceinline__ void syrk_tc_2sm_body(const CUtensorMap &tmap, const 
 #pragma unroll 1
       for (int c0 = half * (TILE / 2); c0 < (half + 1) * (TILE / 2); c0 += 16) {
         double val[16];
-        if (empty_item || (n64 && c0 >= TILE / 2)) {
+        if (empty_item) {
 #pragma unroll
           for (int q = 0; q < 16; q++) val[q] = 0.0;
         } else {
@@ -718,16 +687,14 @@ __device__ __forceinline__ void syrk_tc_2sm_body(const CUtensorMap &tmap, const 
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-    syrk_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b64,
-                       const __grid_constant__ CUtensorMap tmap_b32, TcArgs a) {
-  syrk_tc_2sm_body(tmap, tmap_b64, tmap_b32, a);
+    syrk_tc_2sm_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b64, TcArgs a) {
+  syrk_tc_2sm_body(tmap, tmap_b64, a);
 }
 // the same kernel inside 128 registers per thread (the bound of a 512-thread CTA): 320 x 128 = 40 960 registers leave room
 // for a 96-thread CTA of the observation sweep (248 registers) on the same SM
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
-    syrk_tc_2sm_r128_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b64,
-                            const __grid_constant__ CUtensorMap tmap_b32, TcArgs a) {
-  syrk_tc_2sm_body(tmap, tmap_b64, tmap_b32, a);
+    syrk_tc_2sm_r128_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b64, TcArgs a) {
+  syrk_tc_2sm_body(tmap, tmap_b64, a);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
@@ -842,7 +809,6 @@ struct TcState {
   int n_pairs = 0;
   bool use_pairs = false;
   CUtensorMap map_b64;      // box {64, KS, 1}, 64-byte swizzle: this CTA's half of the B block (2-SM kernel)
-  CUtensorMap map_b32;      // box {32, KS, 1}, 32-byte swizzle: this CTA's half of a 64-column last B block
   int2 *pairs2 = nullptr;   // work list of the 2-SM kernel (every pair shares its B block)
   int n_pairs2 = 0;
   bool use_2sm = false;
@@ -949,17 +915,14 @@ int tensor_syrk_init(balm_ctx *c) {
         rows_of[j1].push_back(j2);                                                  // ... and joins column j1 as A = j2 > B = j1
       }
     }
-    // flag 4: the pair's B block is the last block column and holds at most 64 valid columns -> N = 64 MMAs
-    const bool last_n64 = !getenv("BALM_TC_NO_N64") && c->n - (nb - 1) * TILE <= TILE / 2;
     std::vector<int2> p2;
     for (int bj = 0; bj < nb; bj++) {
       const std::vector<int> &r = rows_of[bj];
-      const int fl = (last_n64 && bj == nb - 1) ? 4 : 0;
       size_t q = 0;
-      for (; q + 1 < r.size(); q += 2) p2.push_back(make_int2(r[q] | (bj << 8) | (r[q + 1] << 16) | (bj << 24), 1 | fl));
+      for (; q + 1 < r.size(); q += 2) p2.push_back(make_int2(r[q] | (bj << 8) | (r[q + 1] << 16) | (bj << 24), 1));
       if (q < r.size()) {  // leftover: duplicate partner, result discarded
         const int other = r[q] + 1 < nb ? r[q] + 1 : r[q];
-        p2.push_back(make_int2(r[q] | (bj << 8) | (other << 16) | (bj << 24), 1 | 2 | fl));
+        p2.push_back(make_int2(r[q] | (bj << 8) | (other << 16) | (bj << 24), 1 | 2));
       }
     }
     st->n_pairs2 = (int)p2.size();
@@ -970,13 +933,6 @@ int tensor_syrk_init(balm_ctx *c) {
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
       balm_set_error("cuTensorMapEncodeTiled (64-byte box) failed");
-      return BALM_ERR_CUDA;
-    }
-    const cuuint32_t box_b32[3] = {32, KS, 1};
-    if (encode(&st->map_b32, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->Gq, dims, strides, box_b32, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-      balm_set_error("cuTensorMapEncodeTiled (32-byte box) failed");
       return BALM_ERR_CUDA;
     }
     const char *e2 = getenv("BALM_TC_2SM");
@@ -1056,7 +1012,7 @@ int tensor_obs_and_syrk(balm_ctx *c, const double *poses, int64_t v0, int64_t v1
     const int items = a.n_pairs * a.splits;
     int clusters = c->sm_count / 2;
     if (items < clusters) clusters = items;
-    syrk_tc_2sm_kernel<<<2 * clusters, TC_THREADS, smem, c->stream>>>(st->map, st->map_b64, st->map_b32, a);
+    syrk_tc_2sm_kernel<<<2 * clusters, TC_THREADS, smem, c->stream>>>(st->map, st->map_b64, a);
     if (cudaGetLastError() != cudaSuccess) {  // cluster launch not possible here: fall back to the 1-SM kernel for good
       st->use_2sm = false;
       a.pairs = st->pairs;
@@ -1106,8 +1062,8 @@ int tensor_overlap_probe(balm_ctx *c, const double *poses, int reps, float *out)
   cudaEvent_t e0, e1, e2;
   cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
   auto syrk = [&](bool r128, cudaStream_t s) {
-    if (r128) syrk_tc_2sm_r128_kernel<<<2 * clusters, TC_THREADS, smem, s>>>(st->map, st->map_b64, st->map_b32, a);
-    else syrk_tc_2sm_kernel<<<2 * clusters, TC_THREADS, smem, s>>>(st->map, st->map_b64, st->map_b32, a);
+    if (r128) syrk_tc_2sm_r128_kernel<<<2 * clusters, TC_THREADS, smem, s>>>(st->map, st->map_b64, a);
+    else syrk_tc_2sm_kernel<<<2 * clusters, TC_THREADS, smem, s>>>(st->map, st->map_b64, a);
   };
   auto sweep = [&](int wpc) {
     return launch_obs_int8(c, poses, 0, c->M, true, st->sc, c->Gq, plane_stride, st->S_dev, SMAX, rows_padded, true, nullptr, wpc);
