@@ -242,17 +242,22 @@ def ref_headers_check(n_poses, m_small, port_eval_s):
     """The reference's OWN divide_thread_left (bavoxel.hpp:1025-1059, compiled from /root/reference's headers against
     stand-in Eigen into oracle/_ref/libbalm_ref.so, when that file travelled here) on the small sample, next to the port's
     time for the same call. A plausibility check of the port's speed, not a baseline: the stand-in has none of Eigen's
-    vectorised kernels, and the reference leaks its per-observation `Co` blocks (bavoxel.hpp:312-320)."""
+    vectorised kernels, and the reference leaks its per-observation `Co` blocks (bavoxel.hpp:312-320) -- which is why it
+    runs in a process of its own: millions of small host allocations inside this one slowed the later e2e leg's
+    balm_set_voxels from 8 ms to 1 s."""
+    code = ("import sys, time, json; sys.path.insert(0, %r); import bench; from oracle import ref_py\n"
+            "if not ref_py.available(): print('null'); sys.exit(0)\n"
+            "rp, pi, ob, co, init = bench.numpy_sample(%d, %d)\n"
+            "prob = ref_py.Problem(%d, rp, pi, ob)\n"
+            "t0 = time.perf_counter(); prob.divide_thread_left(init)\n"
+            "print(json.dumps({'t': time.perf_counter() - t0}))\n") % (ROOT, n_poses, m_small, n_poses)
     try:
-        from oracle import ref_py
-        if not ref_py.available():
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+        res = json.loads(out.stdout.strip().splitlines()[-1])
+        if res is None:
             return None
-        rp, pi, ob, co, init = numpy_sample(n_poses, m_small)
-        prob = ref_py.Problem(n_poses, rp, pi, ob)
-        t0 = time.perf_counter()
-        prob.divide_thread_left(init)
-        return {"ref_headers_standin_eigen_eval_s": time.perf_counter() - t0, "port_eval_s": port_eval_s,
-                "sample_voxels": m_small, "threads": 4}
+        return {"ref_headers_standin_eigen_eval_s": res["t"], "port_eval_s": port_eval_s, "sample_voxels": m_small,
+                "threads": 4}
     except Exception as e:  # the check must never take the bench down
         return {"error": str(e)[:120]}
 
