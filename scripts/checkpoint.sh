@@ -15,10 +15,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"syr
 timeout 240 ncu --set full --clock-control none -k regex:"ldl_dag|ldl_back|solve_residual" -s 6 -c 4 -o gpurun_out/prof_r2_solve -f python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/b3.log 2>&1
 ls -la gpurun_out/*.ncu-rep
 timeout 300 python scripts/assoc_perf.py 2>&1 | tail -3
-python - <<'PY'
-import json
-for f in ("tensor","fp64","c2","c1","reference"):
-    try:
-        d=json.loads(open("gpurun_out/bench_r2_%s.json"%f).read().strip().splitlines()[-1]); print(f, round(d["value"],4), round(d["ms_per_step"],3), {k:round(v,3) for k,v in d.get("phases_ms",{}).items()}, d["e2e"] and round(d["e2e"]["value"],4), d["cpu_baseline"] and d["cpu_baseline"]["value"], d.get("clocks"), d.get("sweeps"))
-    except Exception as e: print(f, "ERR", e)
-PY
+python scripts/print_bench.py
