@@ -56,3 +56,36 @@ def test_shim_runs_reference_call_pattern(prec):
     out = subprocess.run([EXE, str(prec)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "iter0:" in out.stdout and "shim_smoke: residual" in out.stdout  # the reference's trace line (:1132)
+
+
+# ---- the shim on top of the REFERENCE'S OWN tools.hpp (PointCluster, IMUST; stand-in Eigen / PCL of oracle/ref_stubs) ----
+REF_INC = "/root/reference/include"
+EXE3 = os.path.join(ROOT, "tests", "shim_reference_types.bin")
+
+
+def build_reference_types():
+    lib = os.path.join(ROOT, "balm_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++14", "-w", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "oracle", "ref_stubs"), "-I" + REF_INC,
+                           os.path.join(ROOT, "tests", "shim_reference_types.cpp"), "-o", EXE3, "-L" + lib, "-lbalm_b200",
+                           "-Wl,-rpath," + lib, "-ldl", "-lpthread", "-lrt"])
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_INC, "tools.hpp")), reason="/root/reference is not on this box")
+def test_shim_compiles_on_the_reference_types():
+    """#include "tools.hpp" (the reference's, verbatim) + the shim in BALM_B200_WITH_EIGEN mode with its default plptrs type
+    pcl::PointCloud<PointType>::Ptr: what a BALM translation unit looks like after swapping bavoxel.hpp for the shim."""
+    build_reference_types()
+    assert os.path.exists(EXE3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", [0, 1])
+def test_shim_runs_on_the_reference_types(prec):
+    if os.path.exists(os.path.join(REF_INC, "tools.hpp")):
+        build_reference_types()
+    if not os.path.exists(EXE3):
+        pytest.skip("tests/shim_reference_types.bin was not built (needs /root/reference at build time)")
+    out = subprocess.run([EXE3, str(prec)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "shim_reference_types: residual" in out.stdout
