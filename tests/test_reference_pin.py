@@ -36,7 +36,8 @@ def test_exp_log_match_the_reference():
         assert np.abs(ref.log_so3(R) - orc.log_so3(R)).max() <= 1e-12
 
 
-@pytest.mark.parametrize("n_poses,n_planes,drop,with_fix", [(6, 40, 0.0, False), (9, 60, 0.4, False), (8, 30, 0.3, True), (25, 80, 0.0, False)])
+@pytest.mark.parametrize("n_poses,n_planes,drop,with_fix", [(6, 40, 0.0, False), (9, 60, 0.4, False), (8, 30, 0.3, True), (25, 80, 0.0, False),
+                                                            (2, 20, 0.0, False), (3, 20, 0.0, True)])
 def test_evaluators_match_the_reference(n_poses, n_planes, drop, with_fix):
     sc = scenes.make_scene(n_poses=n_poses, n_planes=n_planes, seed=17, drop=drop, with_fix=with_fix, pts_size=12)
     # the reference's push_voxel derives coe = sum of N itself (bavoxel.hpp:42-44): the scene's coe must be that
@@ -161,6 +162,35 @@ def test_append_restatement_matches_the_reference_octree_on_the_voxels_it_keeps(
     extra = [kl for kl in where if kl not in kept]
     assert all(kl not in before for kl in extra)              # nothing that WAS a plane leaf is pushed by the reference only
     assert len(kept) > 0.6 * len(where)
+
+
+def test_repeated_marginalisation_matches_the_reference_octree():
+    """Two window shifts in a row: after the first one many fix clusters hold >= 50 points, so the second exercises the
+    rule that such a leaf no longer absorbs retired scans (to_margi, bavoxel.hpp:790) next to leaves that still do."""
+    n, mg = 10, 2
+    kw = dict(voxel_size=2.0, layer_limit=2, min_ps=15, eigen_value_array=(1 / 16, 1 / 16, 1 / 16))
+    pts, frs, poses = assoc_ref.synthetic_scans(n_poses=n, pts_per_scan=3000, seed=24)
+    poses12 = scenes.pack_poses([r for r, _ in poses], [p for _, p in poses])
+    s = _session_from_scans(pts.astype(np.float32), frs, poses12, n, **kw)
+    keys, rp, pi, ob, fx, co = s.export(n)
+    rng = np.random.default_rng(2)
+    cur = (rp, pi, ob, None)
+    win, x = n, poses12.copy()
+    for step in range(2):
+        x = x.copy()
+        x[:, 9:] += rng.normal(0, 0.005, x.shape[0:1] + (3,))
+        s.marginalize(mg, x, win)                             # x: the window's optimised poses (x_poses)
+        k1, rp1, pi1, ob1, fx1, co1 = s.export(win - mg)
+        r_rp, r_pi, r_ob, r_fx, r_co = assoc_ref.marginalize_ref(win, cur[0], cur[1], cur[2], cur[3], x, mg, kw["min_ps"])
+        assert np.array_equal(rp1, r_rp) and np.array_equal(pi1, r_pi) and np.array_equal(co1, r_co)
+        assert np.array_equal(ob1, r_ob)
+        assert np.abs(fx1 - r_fx).max() <= 1e-12 * np.abs(r_fx).max()
+        if step == 0:
+            big = fx1[:, 9] >= 50
+            assert big.any() and (~big).any()                 # both kinds of leaves go into the second shift
+        cur = (rp1, pi1, ob1, fx1)
+        x = np.vstack([x[mg:], np.tile(x[-1], (mg, 1))])      # the window shifts (consistency.cpp:137-140); the tail is unused
+        win -= mg
 
 
 # ---------------- the consistency experiment (src/simulation/BAs_left.hpp, toolss.hpp) ----------------
