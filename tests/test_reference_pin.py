@@ -193,6 +193,50 @@ def test_repeated_marginalisation_matches_the_reference_octree():
         win -= mg
 
 
+REALWORLD = "/root/reference/datas/benchmark_realworld"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REALWORLD, "alidarPose.csv")), reason="the reference's dataset is not on this box")
+def test_association_restatement_matches_the_reference_octree_on_its_own_dataset():
+    """The first 16 scans of datas/benchmark_realworld (every 4th point), re-anchored to pose 0 and cut with the constants
+    of benchmark_realworld.cpp:163-185 (voxel_size 2, eigen ratios {1/16, 1/16, 1/9} stored as float): real lidar data has
+    heavy-tailed leaves, negative coordinates and ratios that land close to the thresholds."""
+    from balm_b200 import io
+    n = 16
+    R, p, t, scans = io.read_realworld_dir(REALWORLD, max_scans=n)
+    R0, p0 = R[0].copy(), p[0].copy()
+    poses = [(R0.T @ R[i], R0.T @ (p[i] - p0)) for i in range(n)]          # :163-168
+    poses12 = scenes.pack_poses([r for r, _ in poses], [q for _, q in poses])
+    pts = np.concatenate([sc[::4] for sc in scans]).astype(np.float32)
+    frs = np.concatenate([np.full(len(sc[::4]), i, dtype=np.int32) for i, sc in enumerate(scans)])
+    kw = dict(voxel_size=2.0, layer_limit=2, min_ps=15, eigen_value_array=(1 / 16, 1 / 16, 1 / 9))
+    s = _session_from_scans(pts, frs, poses12, n, **kw)
+    keys, rp, pi, ob, fx, co, lay = s.export(n, with_layers=True)
+    rp0, pi0, ob0, co0, keys0, lay0 = assoc_ref.cut_voxels(pts.astype(np.float64), frs, poses, with_layers=True, **kw)
+    assert len(keys) > 200 and len(np.unique(lay)) == 3
+    assert np.array_equal(keys, keys0) and np.array_equal(lay, lay0)
+    assert np.array_equal(rp, rp0) and np.array_equal(pi, pi0) and np.array_equal(co, co0)
+    assert np.all(np.abs(ob - ob0) <= 1e-11 * np.abs(ob0).max(axis=0))
+
+
+@pytest.mark.parametrize("fixture", ["realworld_voxels.npz", "realworld_c5_177.npz"])
+def test_golden_fixtures_are_outputs_of_the_reference_code(fixture):
+    """tests/golden/*.npz (plane voxels cut from the reference's dataset; what the GPU tests are held to per iteration) were
+    written with the oracle's outputs. The reference's own VOX_HESS / BALM2 on the same inputs give the same residual,
+    gradient, Hessian diagonal and final poses -- to rounding -- so the golden vectors ARE reference outputs."""
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fixture))
+    n = int(d["n_poses"])
+    p = ref.Problem(n, d["row_ptr"], d["pose_idx"], d["obs10"])
+    assert p.pushed() == len(d["coe"]) and np.array_equal(p.coeffs(), d["coe"])
+    H, g, r = p.divide_thread_left(d["poses_init"])
+    assert abs(r - float(d["oracle_residual0"])) <= 1e-13 * r
+    assert np.abs(g - d["oracle_g0"]).max() <= 1e-12 * np.abs(g).max()
+    assert np.abs(np.diag(H) - d["oracle_Hdiag0"]).max() <= 1e-12 * np.abs(np.diag(H)).max()
+    assert abs(np.linalg.norm(H) - float(d["oracle_H0_fro"])) <= 1e-12 * np.linalg.norm(H)
+    rot, tra = _pose_err(p.damping_iter(d["poses_init"]), d["oracle_poses"])   # BALM2::damping_iter, the whole loop
+    assert rot <= 1e-10 and tra <= 1e-10, (rot, tra)
+
+
 # ---------------- the consistency experiment (src/simulation/BAs_left.hpp, toolss.hpp) ----------------
 sim = pytest.mark.skipif(not ref.sim_available(), reason="oracle/_ref/libbalm_ref_sim.so not built (needs /root/reference)")
 
