@@ -81,6 +81,21 @@ void ref_left_evaluate_acc2(void *h, const double *poses12, int head, int end, d
   for (int i = 0; i < n; i++) g[i] = JacT[i];
   *residual = r;
 }
+// VOX_HESS::acc_evaluate2(xs, head, end, Hess, JacT, residual): the right-update evaluator (bavoxel.hpp:53-158; dead code in
+// the reference -- its only call site is commented out, :1108 -- but an independent derivation of residual and gradient)
+void ref_acc_evaluate2(void *h, const double *poses12, int head, int end, double *H, double *g, double *residual) {
+  Problem *p = static_cast<Problem *>(h);
+  win_size = p->N;
+  set_poses(p, poses12);
+  const int n = 6 * p->N;
+  Eigen::MatrixXd Hess(n, n);
+  Eigen::VectorXd JacT(n);
+  double r = 0;
+  p->vox.acc_evaluate2(p->xs, head, end, Hess, JacT, r);
+  for (int c = 0; c < n; c++) for (int rr = 0; rr < n; rr++) H[(size_t)c * n + rr] = Hess(rr, c);
+  for (int i = 0; i < n; i++) g[i] = JacT[i];
+  *residual = r;
+}
 // VOX_HESS::evaluate_only_residual
 void ref_evaluate_only_residual(void *h, const double *poses12, double *residual) {
   Problem *p = static_cast<Problem *>(h);

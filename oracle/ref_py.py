@@ -30,6 +30,7 @@ def lib():
         L.ref_problem_coeffs.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_left_evaluate_acc2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_evaluate_only_residual.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.ref_acc_evaluate2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_divide_thread_left.restype = C.c_double
         L.ref_divide_thread_left.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_damping_iter.argtypes = [C.c_void_p, C.c_void_p]
@@ -89,6 +90,16 @@ class Problem:
         g = np.zeros(n)
         r = C.c_double()
         lib().ref_left_evaluate_acc2(self.h, _p(poses12), head, self.pushed() if end is None else end, _p(H), _p(g), C.byref(r))
+        return H, g, r.value
+
+    def acc_evaluate2(self, poses12, head=0, end=None):
+        """The reference's right-update evaluator (bavoxel.hpp:53-158) -> (Hess, JacT, residual)."""
+        n = 6 * self.N
+        poses12 = np.ascontiguousarray(poses12, dtype=np.float64)
+        H = np.zeros((n, n), order="F")
+        g = np.zeros(n)
+        r = C.c_double()
+        lib().ref_acc_evaluate2(self.h, _p(poses12), head, self.pushed() if end is None else end, _p(H), _p(g), C.byref(r))
         return H, g, r.value
 
     def evaluate_only_residual(self, poses12):

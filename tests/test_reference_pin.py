@@ -237,6 +237,21 @@ def test_golden_fixtures_are_outputs_of_the_reference_code(fixture):
     assert rot <= 1e-10 and tra <= 1e-10, (rot, tra)
 
 
+@pytest.mark.parametrize("n_poses,n_planes,drop,with_fix", [(6, 40, 0.0, False), (9, 60, 0.4, True)])
+def test_right_update_restatement_matches_the_reference(n_poses, n_planes, drop, with_fix):
+    """tests/numpy_acc2.py (the second reference-side pin of residual and gradient, used on the oracle and on the GPU path)
+    against the reference's actual VOX_HESS::acc_evaluate2 (bavoxel.hpp:53-158)."""
+    import numpy_acc2 as na
+    sc = scenes.make_scene(n_poses=n_poses, n_planes=n_planes, seed=17, drop=drop, with_fix=with_fix, pts_size=12)
+    coe = np.array([sc["obs10"][a:b, 9].sum() for a, b in zip(sc["row_ptr"][:-1], sc["row_ptr"][1:])])
+    p = ref.Problem(n_poses, sc["row_ptr"], sc["pose_idx"], sc["obs10"], sc["fix10"])
+    for x in (sc["poses_init"], sc["poses_gt"]):
+        Hr, gr, rr = p.acc_evaluate2(x)
+        g, r = na.acc_evaluate2(n_poses, sc["row_ptr"], sc["pose_idx"], sc["obs10"], coe, x, sc["fix10"])
+        assert abs(r - rr) <= 1e-12 * abs(rr)
+        assert np.abs(g - gr).max() <= 1e-12 * np.abs(gr).max()
+
+
 # ---------------- the consistency experiment (src/simulation/BAs_left.hpp, toolss.hpp) ----------------
 sim = pytest.mark.skipif(not ref.sim_available(), reason="oracle/_ref/libbalm_ref_sim.so not built (needs /root/reference)")
 
