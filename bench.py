@@ -205,13 +205,13 @@ class CpuArm:
         k1 = m_small * n_poses
         self.small = orc.Oracle(n_poses, rp[:m_small + 1], pi[:k1], ob[:k1], co[:m_small], native=native)
 
-    def step(self, voxels_total):
+    def step(self, voxels_total, threads=4):
         """-> (seconds of this sample step, extrapolated seconds per LM iteration of the full workload, detail)"""
         t_begin = time.perf_counter()
         te, tr = [], []
         for o in (self.small, self.big):
             t0 = time.perf_counter()
-            H, g, r = o.evaluate_threads(self.init, threads=4)     # divide_thread_left
+            H, g, r = o.evaluate_threads(self.init, threads=threads)     # divide_thread_left (4) / the single-thread twin (1)
             te.append(time.perf_counter() - t0)
             t0 = time.perf_counter()
             o.residual(self.init)                                   # evaluate_only_residual, 1 thread
@@ -270,6 +270,12 @@ def cpu_baseline_once(n_poses, voxels_total, m_small, m_large):
     chk = ref_headers_check(n_poses, m_small, detail["t_eval_s"][0])
     if chk:
         out["ref_headers_check"] = chk
+    if n_poses * voxels_total <= 200000:  # C1: also the single-thread twin of benchmark_virtual.cpp:218-482
+        try:
+            _, t_one, _ = arm.step(voxels_total, threads=1)
+            out["value_single_thread_twin"] = 1.0 / t_one
+        except Exception:
+            pass
     try:  # labelled NON-reference column: the same port compiled with -march=native
         _, t_nat, _ = CpuArm(n_poses, m_small, m_large, native=True).step(voxels_total)
         out["value_march_native"] = 1.0 / t_nat
